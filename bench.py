@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py - fit throughput of the B200 hot path on BASELINE.json's headline configuration.
+
+Workload (N=1): configs[1] = RandomizedPca f32, 10,000,000 x 1024, k=64, 4 power iterations,
+seeded Omega.  One "step" = one complete `RandomizedPca.fit` over the rank's row shard.
+Multi-GPU (torchrun, one process per GPU): rows are sharded, every rank holds its own 10M x 1024
+shard (weak scaling); the fit is collective (NCCL all-reduce of the small replicated matrices).
+
+  value  : samples/s with X resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e    : samples/s through the public API with a pinned HOST X (H2D inside the call) and host outputs
+  roofline, cpu_baseline, clocks, gpu_launches: see the task contract / DESIGN.md
+
+`--impl reference` times the CPU restatement of the reference (oracle/, numpy+OpenBLAS LAPACK,
+all host threads) on a bounded row sample of the same workload (the Rust crate itself cannot be
+built in this image: no cargo/rustc).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 1_234_567_891_011_121_314
+CONFIGS = {
+    # name: (algorithm, dtype, n, d, k, q)
+    "c2": ("rpca", "f32", 10_000_000, 1024, 64, 4),
+    "c1": ("pca", "f64", 10_000, 100, 10, 0),
+    "c3": ("ica", "f32", 1_000_000, 64, 64, 0),
+    "c4s": ("pca", "f64", 2_000_000, 512, 64, 0),
+    "c5s": ("rpca", "f32", 40_000_000, 256, 32, 4),
+}
+METRIC = "fit samples/s (exact/randomized PCA, FastICA) @1/2/4/8 B200; % HBM roofline"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (testing only)")
+    ap.add_argument("--engine", type=int, default=-1, help="f32 engine: 0 SIMT, 1 tcgen05 (default: library default)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic data: low-rank + noise + offsets; same generator family on both arms
+# ---------------------------------------------------------------------------------------------
+def spectrum(rank):
+    return 10.0 * 0.9 ** np.arange(rank)
+
+
+def make_x_device(n, d, dtype, rank_seed, device, algorithm):
+    """Generates the rank's shard on the device in row chunks (torch is data plumbing here)."""
+    import torch
+    tdt = torch.float32 if dtype == "f32" else torch.float64
+    g = torch.Generator(device=device)
+    g.manual_seed(20240607 + rank_seed)
+    gs = torch.Generator(device=device)
+    gs.manual_seed(777)  # shared structure (V, offsets, mixing) identical on every rank
+    x = torch.empty((n, d), dtype=tdt, device=device)
+    chunk = max(1, min(n, (1 << 28) // max(d, 1)))
+    if algorithm == "ica":
+        a = torch.randn((d, d), generator=gs, device=device, dtype=torch.float64)
+        q1, _ = torch.linalg.qr(a)
+        q2, _ = torch.linalg.qr(torch.randn((d, d), generator=gs, device=device, dtype=torch.float64))
+        mix = (q1 * torch.linspace(1.0, 5.0, d, device=device, dtype=torch.float64)) @ q2.T
+        off = torch.rand(d, generator=gs, device=device, dtype=torch.float64) * 2 - 1
+        for r0 in range(0, n, chunk):
+            r1 = min(n, r0 + chunk)
+            m = r1 - r0
+            u = torch.rand((m, d), generator=g, device=device, dtype=torch.float64)
+            lap = -torch.sign(u - 0.5) * torch.log1p(-2 * torch.abs(u - 0.5) + 1e-300) / np.sqrt(2.0)
+            uni = (u * 2 - 1) * np.sqrt(3.0)
+            gn = torch.randn((m, d), generator=g, device=device, dtype=torch.float64)
+            sg = torch.sign(gn) * torch.abs(gn) ** 1.5 / 1.4
+            kind = (torch.arange(d, device=device) % 3)[None, :]
+            s = torch.where(kind == 0, lap, torch.where(kind == 1, uni, sg))
+            x[r0:r1] = (s @ mix.T + off).to(tdt)
+        return x
+    rank = min(d, 128)
+    v, _ = torch.linalg.qr(torch.randn((d, rank), generator=gs, device=device, dtype=torch.float32))
+    sv = (v * torch.tensor(spectrum(rank), device=device, dtype=torch.float32)).T.contiguous()  # rank x d
+    off = torch.rand(d, generator=gs, device=device, dtype=torch.float32) * 2 - 1
+    for r0 in range(0, n, chunk):
+        r1 = min(n, r0 + chunk)
+        z = torch.randn((r1 - r0, rank), generator=g, device=device, dtype=torch.float32)
+        blk = z @ sv
+        blk += 0.1 * torch.randn((r1 - r0, d), generator=g, device=device, dtype=torch.float32)
+        blk += off
+        x[r0:r1] = blk.to(tdt)
+        del z, blk
+    return x
+
+
+def make_x_host(n, d, dtype, algorithm):
+    """numpy version of the same distribution family for the CPU arm (bounded row sample)."""
+    rng = np.random.default_rng(20240607)
+    npdt = np.float32 if dtype == "f32" else np.float64
+    if algorithm == "ica":
+        from tests import synth
+        return synth.mixed_sources(n, d, seed=1, dtype=npdt)[0]
+    rank = min(d, 128)
+    v, _ = np.linalg.qr(rng.standard_normal((d, rank)))
+    x = (rng.standard_normal((n, rank), dtype=np.float32) * spectrum(rank).astype(np.float32)) @ v.T.astype(np.float32)
+    x += 0.1 * rng.standard_normal((n, d), dtype=np.float32)
+    x += rng.uniform(-1, 1, size=d).astype(np.float32)
+    return np.ascontiguousarray(x.astype(npdt))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle) - bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_fit_once(algorithm, x, k, q):
+    from oracle import ica as oica
+    from oracle import pca as opca
+    from oracle.rng import Mcg128Xsl64
+    d = x.shape[1]
+    if algorithm == "rpca":
+        rng = np.random.default_rng(5)
+        omega = rng.standard_normal((d, k + 10)).astype(x.dtype)  # values irrelevant for timing
+        m = opca.RandomizedPca(k, n_iter=q)
+        m.fit(x, omega)
+        return m
+    if algorithm == "pca":
+        m = opca.Pca(k, economy=True)  # economy SVD: the reference's full n x n U cannot be afforded
+        m.fit(x)
+        return m
+    w_init = np.random.default_rng(5).standard_normal((d, d)).astype(x.dtype)
+    m = oica.FastIca()
+    m.fit(x, w_init)
+    return m
+
+
+def cpu_sample_rows(algorithm, d, requested):
+    if requested:
+        return requested
+    if algorithm == "rpca":
+        return max(1000, int(200_000 * 1024 / d))
+    if algorithm == "pca":
+        return max(1000, int(4_000_000 / d))
+    return 200_000
+
+
+def run_cpu(algorithm, dtype, d, k, q, rows, steps, warmup):
+    x = make_x_host(rows, d, dtype, algorithm)
+    for _ in range(min(warmup, 1)):
+        cpu_fit_once(algorithm, x, k, q)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_fit_once(algorithm, x, k, q)
+    dt = (time.perf_counter() - t0) / steps
+    return rows / dt, dt
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    algorithm, dtype, n_cfg, d, k, q = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = args.rows or n_cfg
+    workload = {
+        "c2": "RandomizedPca f32 10Mx1024 k=64 q=4 (configs[1])", "c1": "Pca f64 10000x100 k=10 (configs[0])",
+        "c3": "FastIca logcosh f32 1Mx64 (configs[2])", "c4s": "Pca f64 2Mx512 k=64 (configs[3] at d=512)",
+        "c5s": "RandomizedPca f32 40Mx256 k=32 q=4 (configs[4] per-GPU shard)"}[args.config]
+    config = {"workload": workload, "algorithm": algorithm, "rows_per_gpu": n, "features": d, "n_components": k,
+              "power_iterations": q, "oversamples": 10, "sharding": f"rows x{world}",
+              "l2": "inputs larger than L2 (no flush needed)" if n * d * (4 if dtype == "f32" else 8) > (256 << 20)
+              else "L2 flushed between steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rows = cpu_sample_rows(algorithm, d, args.cpu_rows)
+        val, dt = run_cpu(algorithm, dtype, d, k, q, rows, max(1, args.steps), args.warmup)
+        cores = blas_threads()
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": f"{rows} rows x {d} (oracle restatement of the reference, numpy/OpenBLAS; "
+                                           "Rust crate not buildable here)"},
+                "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import petal_decomposition_b200 as pd
+    from petal_decomposition_b200.dist import init_distributed
+
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ctx = init_distributed()
+    if args.engine >= 0:
+        ctx.set_f32_engine(args.engine)
+    dev = torch.device("cuda", local)
+    npdt = np.float32 if dtype == "f32" else np.float64
+    esize = 4 if dtype == "f32" else 8
+
+    x = make_x_device(n, d, dtype, rank, dev, algorithm)
+    torch.cuda.synchronize()
+
+    def make_model():
+        if algorithm == "rpca":
+            return pd.RandomizedPcaBuilder.new(k).seed(SEED).n_power_iter(q).build()
+        if algorithm == "pca":
+            return pd.Pca.new(k)
+        return pd.FastIca.with_seed(SEED)
+
+    flush = None
+    if n * d * esize <= (256 << 20):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(inp):
+        m = make_model()
+        m.fit(inp)
+        return m
+
+    for _ in range(args.warmup):
+        step(x)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.set_profiling(True)
+    ctx.profile()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    model = None
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        model = step(x)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ctx.launch_count() - launches0
+    prof = ctx.profile()
+    ctx.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    dev_ms = float(tm.item())
+    ms_per_step = dev_ms / args.steps
+    value = n * world / (ms_per_step * 1e-3)
+    n_iter_info = getattr(model, "n_iter", None)
+
+    # ---- e2e: host (pinned) input, H2D inside the call, host outputs ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            n_e2e = n
+            try:
+                xh_t = torch.empty((n_e2e, d), dtype=x.dtype, pin_memory=True)
+            except Exception:
+                n_e2e = max(1, n // 8)
+                xh_t = torch.empty((n_e2e, d), dtype=x.dtype, pin_memory=True)
+            xh_t.copy_(x[:n_e2e])
+            torch.cuda.synchronize()
+            xh = xh_t.numpy()
+            del x
+            torch.cuda.empty_cache()
+            for _ in range(min(args.warmup, 1)):
+                step(xh)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                m = step(xh)
+            barrier()
+            dt = time.perf_counter() - t0
+            te = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dt = float(te.item()) / args.steps
+            d2h = (m.components().nbytes + m.mean().nbytes + m.singular_values().nbytes + esize) \
+                if algorithm != "ica" else (m.components.nbytes + m.means.nbytes)
+            e2e = {"value": n_e2e * world / dt, "unit": "samples/s", "h2d_bytes_per_step": int(n_e2e * d * esize),
+                   "d2h_bytes_per_step": int(d2h), "rows_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
+                   "timing": "wall clock around the public API call (includes H2D of X from pinned host memory)"}
+        except Exception as e:  # host memory too small etc.
+            e2e = {"value": None, "unit": "samples/s", "error": str(e)[:200]}
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (largest total device time in the timed region) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    roof = None
+    if prof:
+        stream_k = {kname: v for kname, v in prof.items() if v.get("work", 0) > 0}
+        if stream_k:
+            top = max(stream_k, key=lambda kn: stream_k[kn]["total_ms"])
+            v = stream_k[top]
+            achieved = v["work"] / (v["total_ms"] * 1e-3) / 1e9
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+                traffic = tj.get(top, {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
+                    "launches": v["count"], "avg_ms": v["total_ms"] / v["count"],
+                    "algorithmic_bytes_per_launch": v["work"] / v["count"],
+                    "kernel_share_of_step": v["total_ms"] / dev_ms,
+                    "all_kernels_ms": {kn: round(vv["total_ms"] / args.steps, 4) for kn, vv in prof.items()}}
+
+    cpu = None
+    if not args.no_cpu:
+        rows = cpu_sample_rows(algorithm, d, args.cpu_rows)
+        val, dt = run_cpu(algorithm, dtype, d, k, q, rows, 1, 1)
+        cpu = {"value": val, "unit": "samples/s", "cores": blas_threads(), "kind": "port",
+               "sample": f"{rows} rows x {d}, one fit ({dt:.1f} s), oracle restatement on numpy/OpenBLAS"}
+
+    line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "wall_ms_per_step": t_wall / args.steps * 1e3}
+    if n_iter_info is not None:
+        line["config"]["ica_iterations"] = n_iter_info
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

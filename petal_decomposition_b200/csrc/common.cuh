@@ -1,0 +1,199 @@
+// Shared host/device plumbing for libpetal_b200: error type, context, device buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/petal_b200.h"
+
+namespace petal {
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define PETAL_CUDA(expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            throw ::petal::Error{PETAL_LINALG_ERROR, std::string("CUDA error: ") +               \
+                                                         cudaGetErrorString(_e) + " (" #expr    \
+                                                         ") at " __FILE__ ":" +                 \
+                                                         std::to_string(__LINE__)};             \
+        }                                                                                       \
+    } while (0)
+
+inline void invalid_input(const std::string& m) { throw Error{PETAL_INVALID_INPUT, m}; }
+inline void linalg_error(const std::string& m) { throw Error{PETAL_LINALG_ERROR, m}; }
+
+struct Comm;  // comm.cuh
+
+}  // namespace petal
+
+// The opaque context of the C ABI.
+struct petal_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    int64_t launches = 0;
+    int f32_engine = 1;  // 0 = SIMT FFMA, 1 = tcgen05 3xTF32 where supported
+    std::string last_error;
+    // optional per-kernel timing (CUDA events on the launch stream), see petal_ctx_profile_json
+    bool profiling = false;
+    struct ProfEntry {
+        const char* name;
+        cudaEvent_t a, b;
+        double work;  // caller-defined work units (bytes) for this launch
+    };
+    std::vector<ProfEntry> prof;
+    petal::Comm* comm = nullptr;
+    int rank = 0;
+    int world = 1;
+};
+
+namespace petal {
+
+// 16-byte vector of T (float4 / double2 worth) that the compiler loads/stores as one LDG/STS.128.
+template <typename T>
+struct alignas(16) Pack {
+    static constexpr int N = 16 / sizeof(T);
+    T v[N];
+};
+
+inline bool is_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+inline bool is_device_pointer(const void* p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// Stream-ordered device buffer.
+template <typename T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DBuf() {}
+    DBuf(petal_ctx* ctx, size_t count) { alloc(ctx, count); }
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    DBuf(DBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; }
+    void alloc(petal_ctx* ctx, size_t count) {
+        release();
+        s = ctx->stream;
+        n = count;
+        if (count == 0) return;
+        PETAL_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), s));
+    }
+    void zero() {
+        if (n) PETAL_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~DBuf() { release(); }
+};
+
+// Input that may live on the host: staged into HBM when needed.
+template <typename T>
+struct DevIn {
+    const T* p = nullptr;
+    DBuf<T> staged;
+    size_t bytes_h2d = 0;
+    DevIn() {}
+    DevIn(petal_ctx* ctx, const T* user, size_t count) { set(ctx, user, count); }
+    void set(petal_ctx* ctx, const T* user, size_t count) {
+        if (user == nullptr || count == 0) {
+            p = user;
+            return;
+        }
+        if (is_device_pointer(user)) {
+            p = user;
+        } else {
+            staged.alloc(ctx, count);
+            PETAL_CUDA(cudaMemcpyAsync(staged.p, user, count * sizeof(T), cudaMemcpyHostToDevice,
+                                       ctx->stream));
+            p = staged.p;
+            bytes_h2d = count * sizeof(T);
+        }
+    }
+};
+
+// Output that may live on the host: written to HBM, copied back by commit().
+template <typename T>
+struct DevOut {
+    T* p = nullptr;  // device pointer to write
+    T* user = nullptr;
+    size_t n = 0;
+    bool to_host = false;
+    DBuf<T> staged;
+    DevOut() {}
+    DevOut(petal_ctx* ctx, T* user_ptr, size_t count) { set(ctx, user_ptr, count); }
+    void set(petal_ctx* ctx, T* user_ptr, size_t count) {
+        user = user_ptr;
+        n = count;
+        if (user == nullptr || count == 0) {
+            p = nullptr;
+            return;
+        }
+        if (is_device_pointer(user)) {
+            p = user;
+        } else {
+            staged.alloc(ctx, count);
+            p = staged.p;
+            to_host = true;
+        }
+    }
+    explicit operator bool() const { return p != nullptr; }
+    void commit(petal_ctx* ctx) {
+        if (to_host && n)
+            PETAL_CUDA(cudaMemcpyAsync(user, p, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+};
+
+// RAII event pair around one kernel launch (or a launch sequence) when profiling is on.
+struct KTimer {
+    petal_ctx* ctx;
+    int idx = -1;
+    KTimer(petal_ctx* c, const char* name, double work = 0.0) : ctx(c) {
+        if (!c->profiling) return;
+        petal_ctx::ProfEntry e;
+        e.name = name;
+        e.work = work;
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+        cudaEventRecord(e.a, c->stream);
+        c->prof.push_back(e);
+        idx = (int)c->prof.size() - 1;
+    }
+    ~KTimer() {
+        if (idx >= 0) cudaEventRecord(ctx->prof[idx].b, ctx->stream);
+    }
+};
+
+template <typename T>
+inline const char* kname(const char* f32, const char* f64) {
+    return sizeof(T) == 4 ? f32 : f64;
+}
+
+inline void check_launch(petal_ctx* ctx) {
+    ctx->launches++;
+    PETAL_CUDA(cudaGetLastError());
+}
+
+}  // namespace petal

@@ -1,0 +1,839 @@
+// libpetal_b200 - C ABI implementation: the fit / transform flows of exact PCA, randomized PCA
+// and FastICA, assembled from the streaming kernels (stream_kernels.cuh, tc_kernels.cuh) and the
+// small on-device factorizations (small_linalg.cuh).  See include/petal_b200.h for the contract
+// and DESIGN.md for the data layout and per-kernel rooflines.
+#include <algorithm>
+#include <mutex>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "small_linalg.cuh"
+#include "stream_kernels.cuh"
+
+using namespace petal;
+
+namespace {
+
+std::string g_global_error;
+std::mutex g_global_mutex;
+
+template <typename F>
+int guarded(petal_ctx* ctx, F&& f) {
+    if (!ctx) return PETAL_INVALID_INPUT;
+    try {
+        PETAL_CUDA(cudaSetDevice(ctx->device));
+        f();
+        return PETAL_OK;
+    } catch (const Error& e) {
+        ctx->last_error = e.msg;
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::exception& e) {
+        ctx->last_error = std::string("internal error: ") + e.what();
+        return PETAL_LINALG_ERROR;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// tiny kernels used by the flows
+// ---------------------------------------------------------------------------------------
+__global__ void set_value_kernel(double* p, double v) { *p = v; }
+
+template <typename T>
+__global__ void finish_mean_kernel(const double* __restrict__ sum, double inv_n, int64_t d,
+                                   double* __restrict__ mean_d, T* __restrict__ mean_t) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    double m = sum[j] * inv_n;
+    T mt = (T)m;
+    mean_t[j] = mt;
+    mean_d[j] = (double)mt;  // the mean that is actually subtracted (type A, like the reference)
+}
+
+__global__ void trace_kernel(const double* __restrict__ G, int64_t d, double* __restrict__ out) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < d; i += blockDim.x) s += G[i * d + i];
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < blockDim.x; ++i) t += red[i];
+        *out = t;
+    }
+}
+
+// out[j] = (T) sqrt(max(lambda[j], 0))
+template <typename T>
+__global__ void sqrt_cast_kernel(const double* __restrict__ lam, int64_t k, T* __restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < k) out[j] = (T)sqrt(fmax(lam[j], 0.0));
+}
+
+// combine per-rank (absmax, idx, sign) triples: first rank with the strictly larger |.| wins
+__global__ void combine_absmax_kernel(const double* __restrict__ gathered, int world, int64_t k,
+                                      double* __restrict__ out3) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= k) return;
+    double ba = gathered[j * 3 + 0], bi = gathered[j * 3 + 1], bs = gathered[j * 3 + 2];
+    for (int r = 1; r < world; ++r) {
+        const double* g = gathered + ((int64_t)r * k + j) * 3;
+        if (g[0] > ba) {
+            ba = g[0];
+            bi = g[1];
+            bs = g[2];
+        }
+    }
+    out3[j * 3 + 0] = ba;
+    out3[j * 3 + 1] = bi;
+    out3[j * 3 + 2] = bs;
+}
+
+// K[i][j] = Jt[i][j] / sqrt(lambda[i]) * scale   (whitening matrix, reference src/ica.rs:190-203)
+__global__ void whitening_kernel(const double* __restrict__ Jt, const double* __restrict__ lam, int64_t nc,
+                                 int64_t d, double scale, double* __restrict__ K) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nc * d) return;
+    int64_t i = idx / d;
+    double l = lam[i];
+    K[idx] = (l > 0.0) ? Jt[idx] * rsqrt(l) * scale : 0.0;
+}
+
+// Gd[i][j] = HK[i][j] * inv_n - gp[i] * inv_n * W[i][j]     (reference src/ica.rs:334-342)
+__global__ void ica_gd_kernel(const double* __restrict__ HK, const double* __restrict__ gp,
+                              const double* __restrict__ W, int64_t nc, double inv_n, double* __restrict__ Gd) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nc * nc) return;
+    int64_t i = idx / nc;
+    Gd[idx] = HK[idx] * inv_n - gp[i] * inv_n * W[idx];
+}
+
+// lim = max_i | |sum_j W1[i][j] * (variant ? W[j][i] : W[i][j])| - 1 |   (reference src/ica.rs:344-354)
+__global__ void ica_lim_kernel(const double* __restrict__ W1, const double* __restrict__ W, int nc, int variant,
+                               double* __restrict__ lim) {
+    __shared__ double red[256];
+    double best = 0.0;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < nc; ++j) s += W1[(int64_t)i * nc + j] * (variant ? W[(int64_t)j * nc + i] : W[(int64_t)i * nc + j]);
+        double v = fabs(fabs(s) - 1.0);
+        if (v > best || v != v) best = v;
+    }
+    red[threadIdx.x] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+        for (int i = 0; i < blockDim.x; ++i)
+            if (red[i] > b || red[i] != red[i]) b = red[i];
+        *lim = b;
+    }
+}
+
+__global__ void scale_cols_kernel(double* __restrict__ S, int64_t rows, int64_t cols,
+                                  const double* __restrict__ sig) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < rows * cols) S[idx] *= sig[idx % cols];
+}
+
+// ---------------------------------------------------------------------------------------
+// shared pieces of the flows
+// ---------------------------------------------------------------------------------------
+inline void launch1(petal_ctx* ctx) { check_launch(ctx); }
+
+int64_t global_rows(petal_ctx* ctx, int64_t n) {
+    if (ctx->world <= 1) return n;
+    DBuf<double> cnt(ctx, 1);
+    set_value_kernel<<<1, 1, 0, ctx->stream>>>(cnt.p, (double)n);
+    launch1(ctx);
+    allreduce_sum(ctx, cnt.p, 1);
+    double h = 0.0;
+    PETAL_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return (int64_t)(h + 0.5);
+}
+
+template <typename T>
+struct ColMean {
+    DBuf<double> mean_d;
+    DBuf<T> mean_t;
+    const T* mu = nullptr;  // nullptr when centering is off
+};
+
+// reference: input.mean_axis(Axis(0)) (src/pca.rs:207,521; src/ica.rs:174)
+template <typename T>
+void compute_mean(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, bool centering,
+                  ColMean<T>& out) {
+    out.mean_d.alloc(ctx, (size_t)d);
+    out.mean_t.alloc(ctx, (size_t)d);
+    out.mean_d.zero();
+    out.mean_t.zero();
+    out.mu = nullptr;
+    if (!centering || d == 0) return;
+    DBuf<double> sum(ctx, (size_t)d);
+    sum.zero();
+    launch_colsum<T>(ctx, X, n, d, d, sum.p);
+    allreduce_sum(ctx, sum.p, (size_t)d);
+    finish_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, 1.0 / (double)n_total, d,
+                                                                               out.mean_d.p, out.mean_t.p);
+    launch1(ctx);
+    out.mu = out.mean_t.p;
+}
+
+// G[d x d] (f64) = (X - mu)^T (X - mu), all-reduced over ranks and mirrored.
+template <typename T>
+void centered_gram(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G) {
+    PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
+    AtbParams<T> p{};
+    p.A = X; p.lda = ld; p.da = d; p.mua = mu;
+    p.B = X; p.ldb = ld; p.db = d; p.mub = mu;
+    p.n = n; p.C = G; p.ldc = d; p.symmetric = 1;
+    launch_atb<T>(ctx, p);
+    allreduce_sum(ctx, G, (size_t)(d * d));
+    launch_symmetrize(ctx, G, d);
+}
+
+template <typename T>
+void gemm_xb(petal_ctx* ctx, const T* A, int64_t lda, int64_t n, int64_t K, const T* B, int64_t ldb,
+             bool b_trans, int64_t L, const T* mu, const T* bias, T* Y, int64_t ldy, double* sumsq = nullptr) {
+    XbParams<T> p{};
+    p.A = A; p.lda = lda; p.n = n; p.K = K; p.B = B; p.ldb = ldb; p.b_trans = b_trans ? 1 : 0; p.L = L;
+    p.mu = mu; p.bias = bias; p.Y = Y; p.ldy = ldy; p.sumsq = sumsq;
+    launch_xb<T>(ctx, p);
+}
+
+// C[da x db] (f64, zeroed here) = (A - mua)^T (B - mub)
+template <typename T>
+void gemm_atb(petal_ctx* ctx, const T* A, int64_t lda, int64_t da, const T* mua, const T* B, int64_t ldb,
+              int64_t db, const T* mub, int64_t n, double* C) {
+    PETAL_CUDA(cudaMemsetAsync(C, 0, (size_t)(da * db) * sizeof(double), ctx->stream));
+    AtbParams<T> p{};
+    p.A = A; p.lda = lda; p.da = da; p.mua = mua; p.B = B; p.ldb = ldb; p.db = db; p.mub = mub;
+    p.n = n; p.C = C; p.ldc = db; p.symmetric = 0;
+    launch_atb<T>(ctx, p);
+}
+
+template <typename T>
+double rank_cutoff() {
+    // eigenvalues of a Gram matrix below cutoff * lambda_max are treated as numerically zero
+    double eps = (sizeof(T) == 4) ? 1.1920929e-07 : 2.220446049250313e-16;
+    double c = 8.0 * eps;
+    return std::max(c * c, 1e-13);
+}
+
+// Orthonormal basis (f64) of the range of Z[rows x l] via two rounds of Gram + Jacobi eigh
+// (robust to rank deficiency: null directions become zero columns).  In place.
+// Plays the role of the reference's re-normalisation between power iterations
+// (lu::Factorized::into_pl, src/pca.rs:709-713) - same range, better conditioned.
+void orthonormalize_columns(petal_ctx* ctx, double* Z, int64_t rows, int64_t l, double cutoff) {
+    DBuf<double> G(ctx, (size_t)(l * l)), Jt(ctx, (size_t)(l * l)), sig(ctx, (size_t)l), P(ctx, (size_t)(l * l));
+    DBuf<double> Z1(ctx, (size_t)(rows * l));
+    for (int round = 0; round < 2; ++round) {
+        gemm_atb<double>(ctx, Z, l, l, nullptr, Z, l, l, nullptr, rows, G.p);
+        jacobi_rows(ctx, G.p, l, l, nullptr, Jt.p, sig.p);
+        launch_scaled_transpose(ctx, Jt.p, sig.p, l, 0, round == 0 ? cutoff : 1e-6, P.p);
+        gemm_xb<double>(ctx, Z, l, rows, l, P.p, l, false, l, nullptr, nullptr, Z1.p, l);
+        PETAL_CUDA(cudaMemcpyAsync(Z, Z1.p, (size_t)(rows * l) * sizeof(double), cudaMemcpyDeviceToDevice,
+                                   ctx->stream));
+    }
+}
+
+// svd_flip (reference src/pca.rs:815-850) on the k leading columns: decides each sign from the
+// max-|.| entry of the score column (same sign as the U column since sigma >= 0), first row
+// wins, across all ranks; flips score columns and component rows.
+template <typename T>
+void flip_signs(petal_ctx* ctx, T* scores, int64_t n, int64_t k, T* comps, int64_t d) {
+    if (k == 0) return;
+    DBuf<double> local3(ctx, (size_t)(k * 3));
+    launch_colabsmax<T>(ctx, scores, n, k, k, local3.p);
+    double* flip3 = local3.p;
+    DBuf<double> gathered, out3;
+    if (ctx->world > 1) {
+        gathered.alloc(ctx, (size_t)(ctx->world * k * 3));
+        out3.alloc(ctx, (size_t)(k * 3));
+        allgather(ctx, local3.p, gathered.p, (size_t)(k * 3));
+        combine_absmax_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(gathered.p, ctx->world, k, out3.p);
+        launch1(ctx);
+        flip3 = out3.p;
+    }
+    launch_apply_flip<T>(ctx, scores, n, k, k, comps, d, flip3);
+}
+
+void finish_call(petal_ctx* ctx, bool any_host_output) {
+    if (any_host_output) PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+std::string dim_message(int64_t k) { return "every dimension should be at least " + std::to_string(k); }
+
+// ---------------------------------------------------------------------------------------
+// exact PCA  (reference Pca::inner_fit, src/pca.rs:195-231)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, bool centering, T* comps_u,
+             T* mean_u, T* sing_u, T* tv_u, T* scores_u) {
+    if (n < 0 || d < 0 || k < 0) invalid_input("negative dimension");
+    const int64_t n_total = global_rows(ctx, n);
+    if (n_total < k || d < k) invalid_input(dim_message(k));  // src/pca.rs:199-204
+    if (n_total == 0) return;                                  // src/pca.rs:207-211
+    if (d == 0) return;
+
+    DevIn<T> X(ctx, x_user, (size_t)(n * d));
+    DevOut<T> comps(ctx, comps_u, (size_t)(k * d)), mean(ctx, mean_u, (size_t)d), sing(ctx, sing_u, (size_t)k),
+        tv(ctx, tv_u, 1), scores(ctx, scores_u, (size_t)(n * k));
+
+    ColMean<T> cm;
+    compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
+
+    // Gram of the centred data; its eigen-decomposition G = V diag(sigma^2) V^T gives what the
+    // reference takes from gesvd (src/pca.rs:216-220): sigma and Vt.  The n x n U is never formed.
+    DBuf<double> G(ctx, (size_t)(d * d)), Jt(ctx, (size_t)(d * d)), lam(ctx, (size_t)d), tvd(ctx, 1);
+    centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
+    trace_kernel<<<1, 256, 0, ctx->stream>>>(G.p, d, tvd.p);  // sum of all sigma^2, src/pca.rs:224
+    launch1(ctx);
+    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p);
+
+    DBuf<T> comps_tmp;
+    T* comps_dev = comps.p;
+    if (!comps_dev) {
+        comps_tmp.alloc(ctx, (size_t)(k * d));
+        comps_dev = comps_tmp.p;
+    }
+    launch_cast<double, T>(ctx, Jt.p, comps_dev, k * d);  // components = vt[0..k] (src/pca.rs:225)
+
+    if (k > 0) {
+        // scores = Xc * V_k^T = U_k * sigma_k (transform_with_u, src/pca.rs:758-779); also the
+        // carrier of the u-based sign decision of svd_flip.
+        DBuf<T> scores_tmp;
+        T* scores_dev = scores.p;
+        if (!scores_dev) {
+            scores_tmp.alloc(ctx, (size_t)(n * k));
+            scores_dev = scores_tmp.p;
+        }
+        gemm_xb<T>(ctx, X.p, d, n, d, comps_dev, d, true, k, cm.mu, nullptr, scores_dev, k);
+        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d);
+        if (sing) {
+            sqrt_cast_kernel<T><<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(lam.p, k, sing.p);
+            launch1(ctx);
+        }
+    }
+    if (mean) launch_cast<T, T>(ctx, cm.mean_t.p, mean.p, d);
+    if (tv) launch_cast<double, T>(ctx, tvd.p, tv.p, 1);
+
+    comps.commit(ctx); mean.commit(ctx); sing.commit(ctx); tv.commit(ctx); scores.commit(ctx);
+    finish_call(ctx, comps.to_host || mean.to_host || sing.to_host || tv.to_host || scores.to_host);
+}
+
+// ---------------------------------------------------------------------------------------
+// randomized PCA  (reference RandomizedPca::inner_fit / randomized_svd / randomized_range_finder,
+//                  src/pca.rs:509-550, 668-718)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, bool centering,
+              int64_t n_over, int64_t n_iter, const T* omega_user, T* comps_u, T* mean_u, T* sing_u, T* tv_u,
+              T* scores_u) {
+    if (n < 0 || d < 0 || k < 0 || n_over < 0 || n_iter < 0) invalid_input("negative dimension");
+    const int64_t n_total = global_rows(ctx, n);
+    if (n_total < k || d < k) invalid_input(dim_message(k));  // src/pca.rs:513-518
+    if (n_total == 0 || d == 0) return;                        // src/pca.rs:521-525
+    if (omega_user == nullptr) invalid_input("omega (d x (k + n_oversamples) test matrix) is required");
+    const int64_t l_full = k + n_over;                         // src/pca.rs:679
+    // working width: the reference shrinks to min(rows, cols) after the first product
+    // (src/pca.rs:710,713); we use the leading l columns of Omega from the start.
+    const int64_t l = std::min<int64_t>(l_full, std::min<int64_t>(n_total, d));
+    if (l == 0) return;
+
+    DevIn<T> X(ctx, x_user, (size_t)(n * d));
+    DevIn<T> Omega(ctx, omega_user, (size_t)(d * l_full));
+    DevOut<T> comps(ctx, comps_u, (size_t)(k * d)), mean(ctx, mean_u, (size_t)d), sing(ctx, sing_u, (size_t)k),
+        tv(ctx, tv_u, 1), scores(ctx, scores_u, (size_t)(n * k));
+
+    ColMean<T> cm;
+    compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
+    const double cutoff = rank_cutoff<T>();
+
+    // Y = Xc * Omega (src/pca.rs:707), fused with ||Xc||_F^2 (src/pca.rs:533)
+    DBuf<T> Y(ctx, (size_t)(n * l));
+    DBuf<double> small(ctx, (size_t)(l * l + d * l + 1));  // [G2 | C' | tv] reduced together
+    double* G2 = small.p;
+    double* Cp = small.p + l * l;
+    double* tvd = small.p + l * l + d * l;
+    PETAL_CUDA(cudaMemsetAsync(tvd, 0, sizeof(double), ctx->stream));
+    gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, l, tvd);
+
+    // power iterations (src/pca.rs:708-715): Z = Xc^T Y, re-orthonormalise, Y = Xc Z
+    DBuf<double> Zd(ctx, (size_t)(d * l));
+    DBuf<T> Zt(ctx, (size_t)(d * l));
+    for (int64_t it = 0; it < n_iter; ++it) {
+        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, l, l, nullptr, n, Zd.p);
+        allreduce_sum(ctx, Zd.p, (size_t)(d * l));
+        orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
+        launch_cast<double, T>(ctx, Zd.p, Zt.p, d * l);
+        gemm_xb<T>(ctx, X.p, d, n, d, Zt.p, l, false, l, cm.mu, nullptr, Y.p, l);
+    }
+
+    // thin QR of Y (src/pca.rs:716) done implicitly in two Gram rounds (CholeskyQR2-style, with a
+    // Jacobi eigensolver instead of Cholesky so that rank-deficient Y is handled):
+    //   round 1: Y1 = Y * P1 (materialised),  round 2: Q = Y1 * P2 (implicit)
+    DBuf<double> G1(ctx, (size_t)(l * l)), JtG(ctx, (size_t)(l * l)), sigG(ctx, (size_t)l), P(ctx, (size_t)(l * l));
+    DBuf<T> Pt(ctx, (size_t)(l * l));
+    DBuf<T> Y1(ctx, (size_t)(n * l));
+    gemm_atb<T>(ctx, Y.p, l, l, nullptr, Y.p, l, l, nullptr, n, G1.p);
+    allreduce_sum(ctx, G1.p, (size_t)(l * l));
+    jacobi_rows(ctx, G1.p, l, l, nullptr, JtG.p, sigG.p);
+    launch_scaled_transpose(ctx, JtG.p, sigG.p, l, 0, cutoff, P.p);
+    launch_cast<double, T>(ctx, P.p, Pt.p, l * l);
+    gemm_xb<T>(ctx, Y.p, l, n, l, Pt.p, l, false, l, nullptr, nullptr, Y1.p, l);
+    // B = Q^T Xc (src/pca.rs:681) = P2^T (Y1^T Xc):  C' = Xc^T Y1 (d x l) in one pass over X
+    gemm_atb<T>(ctx, Y1.p, l, l, nullptr, Y1.p, l, l, nullptr, n, G2);
+    gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, l, l, nullptr, n, Cp);
+    allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
+    jacobi_rows(ctx, G2, l, l, nullptr, JtG.p, sigG.p);
+    launch_scaled_transpose(ctx, JtG.p, sigG.p, l, 0, 1e-6, P.p);  // P2 (l x l)
+    DBuf<double> M1(ctx, (size_t)(d * l)), Bm(ctx, (size_t)(l * d));
+    gemm_xb<double>(ctx, Cp, l, d, l, P.p, l, false, l, nullptr, nullptr, M1.p, l);
+    launch_transpose(ctx, M1.p, d, l, Bm.p);  // B (l x d)
+
+    // SVD of B (src/pca.rs:682, gesdd): rows of Jt*B orthogonal
+    DBuf<double> Bout(ctx, (size_t)(l * d)), JtB(ctx, (size_t)(l * l)), sigB(ctx, (size_t)l), Vt(ctx, (size_t)(l * d));
+    jacobi_rows(ctx, Bm.p, l, d, Bout.p, JtB.p, sigB.p);
+    launch_normalize_rows(ctx, Bout.p, sigB.p, l, d, 0.0, Vt.p);
+
+    DBuf<T> comps_tmp;
+    T* comps_dev = comps.p;
+    if (!comps_dev) {
+        comps_tmp.alloc(ctx, (size_t)(k * d));
+        comps_dev = comps_tmp.p;
+    }
+    launch_cast<double, T>(ctx, Vt.p, comps_dev, k * d);  // components = vt[0..k] (src/pca.rs:544)
+
+    if (k > 0) {
+        // U * Sigma = Q * U_B * Sigma (src/pca.rs:683, transform_with_u) = Y1 * (P2 * U_B[:, :k] * Sigma_k)
+        DBuf<double> S(ctx, (size_t)(l * k));
+        DBuf<T> St(ctx, (size_t)(l * k));
+        gemm_xb<double>(ctx, P.p, l, l, l, JtB.p, l, true, k, nullptr, nullptr, S.p, k);
+        scale_cols_kernel<<<(unsigned)ceil_div(l * k, 256), 256, 0, ctx->stream>>>(S.p, l, k, sigB.p);
+        launch1(ctx);
+        launch_cast<double, T>(ctx, S.p, St.p, l * k);
+        DBuf<T> scores_tmp;
+        T* scores_dev = scores.p;
+        if (!scores_dev) {
+            scores_tmp.alloc(ctx, (size_t)(n * k));
+            scores_dev = scores_tmp.p;
+        }
+        gemm_xb<T>(ctx, Y1.p, l, n, l, St.p, k, false, k, nullptr, nullptr, scores_dev, k);
+        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d);  // svd_flip, src/pca.rs:684
+        if (sing) launch_cast<double, T>(ctx, sigB.p, sing.p, k);
+    }
+    if (mean) launch_cast<T, T>(ctx, cm.mean_t.p, mean.p, d);
+    if (tv) launch_cast<double, T>(ctx, tvd, tv.p, 1);
+
+    comps.commit(ctx); mean.commit(ctx); sing.commit(ctx); tv.commit(ctx); scores.commit(ctx);
+    finish_call(ctx, comps.to_host || mean.to_host || sing.to_host || tv.to_host || scores.to_host);
+}
+
+// ---------------------------------------------------------------------------------------
+// transform / inverse_transform (reference src/pca.rs:726-750, 788-811; src/ica.rs:120-131)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+void transform(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, const T* comps_user, int64_t k,
+               const T* mean_user, T* out_user) {
+    if (n < 0 || d < 0 || k < 0) invalid_input("negative dimension");
+    if (n == 0 || k == 0) return;
+    DevIn<T> X(ctx, x_user, (size_t)(n * d)), C(ctx, comps_user, (size_t)(k * d)), mu(ctx, mean_user, (size_t)d);
+    DevOut<T> out(ctx, out_user, (size_t)(n * k));
+    if (!out) invalid_input("output buffer is null");
+    gemm_xb<T>(ctx, X.p, d, n, d, C.p, d, true, k, mu.p, nullptr, out.p, k);
+    out.commit(ctx);
+    finish_call(ctx, out.to_host);
+}
+
+template <typename T>
+void inverse_transform(petal_ctx* ctx, const T* y_user, int64_t n, int64_t k, const T* comps_user, int64_t d,
+                       const T* mean_user, T* out_user) {
+    if (n < 0 || d < 0 || k < 0) invalid_input("negative dimension");
+    if (n == 0 || d == 0) return;
+    DevIn<T> Y(ctx, y_user, (size_t)(n * k)), C(ctx, comps_user, (size_t)(k * d)), mu(ctx, mean_user, (size_t)d);
+    DevOut<T> out(ctx, out_user, (size_t)(n * d));
+    if (!out) invalid_input("output buffer is null");
+    gemm_xb<T>(ctx, Y.p, k, n, k, C.p, d, false, d, nullptr, mu.p, out.p, d);
+    out.commit(ctx);
+    finish_call(ctx, out.to_host);
+}
+
+// ---------------------------------------------------------------------------------------
+// FastICA
+// ---------------------------------------------------------------------------------------
+// symmetric_decorrelation (reference src/ica.rs:363-381): (W W^T)^-1/2 W = polar factor of W,
+// from the one-sided Jacobi of W's rows:  Jt W = diag(s) N  ->  result = Jt^T N.
+void symmetric_decorrelation(petal_ctx* ctx, const double* W, int64_t m, double* out) {
+    DBuf<double> Aout(ctx, (size_t)(m * m)), Jt(ctx, (size_t)(m * m)), sig(ctx, (size_t)m), N(ctx, (size_t)(m * m));
+    jacobi_rows(ctx, W, m, m, Aout.p, Jt.p, sig.p);
+    launch_normalize_rows(ctx, Aout.p, sig.p, m, m, 0.0, N.p);
+    gemm_atb<double>(ctx, Jt.p, m, m, nullptr, N.p, m, m, nullptr, m, out);
+}
+
+// ica_par (reference src/ica.rs:319-361) on data X[n x d] with whitening folded in:
+// the whitened sample is x1 = K1 (x - mu) with K1 = sqrt(n) K (nc x d); K1 == nullptr means the
+// data is already white (d == nc).  Returns W (nc x nc, f64, device) and the iteration count.
+template <typename T>
+void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, const T* mu, const double* K1,
+             int64_t nc, int fun, double tol, int64_t max_iter, int lim_variant, const double* w_init, double* W,
+             int64_t* n_iter_out, double* lim_out) {
+    if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
+    symmetric_decorrelation(ctx, w_init, nc, W);  // src/ica.rs:329
+    DBuf<double> Wk(ctx, (size_t)(nc * d)), Hg(ctx, (size_t)(nc * d + nc)), HK(ctx, (size_t)(nc * nc)),
+        Gd(ctx, (size_t)(nc * nc)), W1(ctx, (size_t)(nc * nc)), limd(ctx, 1);
+    DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, (size_t)(n * nc));
+    double* H = Hg.p;
+    double* gp = Hg.p + nc * d;
+    const double inv_n = 1.0 / (double)n_total;
+    int64_t iters = max_iter;
+    double lim = 0.0;
+    for (int64_t it = 0; it < max_iter; ++it) {
+        // W~ = W K1 so that W x1 = W~ (x - mu): the whitened copy is never materialised
+        const double* Wfull = W;
+        if (K1) {
+            gemm_xb<double>(ctx, W, nc, nc, nc, K1, d, false, d, nullptr, nullptr, Wk.p, d);
+            Wfull = Wk.p;
+        }
+        launch_cast<double, T>(ctx, Wfull, Wt.p, nc * d);
+        // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
+        gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
+        // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
+        PETAL_CUDA(cudaMemsetAsync(gp, 0, (size_t)nc * sizeof(double), ctx->stream));
+        launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp);
+        // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening]
+        PETAL_CUDA(cudaMemsetAsync(H, 0, (size_t)(nc * d) * sizeof(double), ctx->stream));
+        {
+            AtbParams<T> p{};
+            p.A = U.p; p.lda = nc; p.da = nc; p.mua = nullptr; p.B = X; p.ldb = d; p.db = d; p.mub = mu;
+            p.n = n; p.C = H; p.ldc = d; p.symmetric = 0;
+            launch_atb<T>(ctx, p);
+        }
+        allreduce_sum(ctx, Hg.p, (size_t)(nc * d + nc));
+        // Gd = (H K1^T) / n - diag(mean g') W   (src/ica.rs:334-342)
+        const double* HKp = H;
+        if (K1) {
+            gemm_xb<double>(ctx, H, d, nc, d, K1, d, true, nc, nullptr, nullptr, HK.p, nc);
+            HKp = HK.p;
+        }
+        ica_gd_kernel<<<(unsigned)ceil_div(nc * nc, 256), 256, 0, ctx->stream>>>(HKp, gp, W, nc, inv_n, Gd.p);
+        launch1(ctx);
+        symmetric_decorrelation(ctx, Gd.p, nc, W1.p);  // src/ica.rs:343
+        ica_lim_kernel<<<1, 256, 0, ctx->stream>>>(W1.p, W, (int)nc, lim_variant, limd.p);
+        launch1(ctx);
+        PETAL_CUDA(cudaMemcpyAsync(W, W1.p, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        PETAL_CUDA(cudaMemcpyAsync(&lim, limd.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (lim < tol) {  // src/ica.rs:355-357
+            iters = it + 1;
+            break;
+        }
+    }
+    *n_iter_out = iters;
+    if (lim_out) *lim_out = lim;
+}
+
+template <typename T>
+void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun, double tol, int64_t max_iter,
+                 int lim_variant, const T* w_init_user, T* comps_u, T* mean_u, int64_t* n_iter_u, double* lim_u,
+                 T* sources_u) {
+    if (n < 0 || d < 0 || max_iter < 0) invalid_input("negative dimension");
+    const int64_t n_total = global_rows(ctx, n);
+    if (n_total == 0 || d == 0) return;  // src/ica.rs:174-176
+    const int64_t nc = std::min<int64_t>(n_total, d);  // src/ica.rs:173
+    if (w_init_user == nullptr) invalid_input("w_init (nc x nc) is required");
+
+    DevIn<T> X(ctx, x_user, (size_t)(n * d));
+    DevIn<T> Winit(ctx, w_init_user, (size_t)(nc * nc));
+    DevOut<T> comps(ctx, comps_u, (size_t)(nc * d)), mean(ctx, mean_u, (size_t)d), sources(ctx, sources_u, (size_t)(n * nc));
+
+    ColMean<T> cm;
+    compute_mean<T>(ctx, X.p, n, d, n_total, true, cm);
+
+    // whitening (src/ica.rs:189-208): the reference takes U, sigma from gesvd of the d x n centred
+    // matrix; the same U, sigma^2 are the eigenpairs of the d x d Gram Xc^T Xc.
+    DBuf<double> G(ctx, (size_t)(d * d)), Jt(ctx, (size_t)(d * d)), lam(ctx, (size_t)d);
+    centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
+    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p);
+    DBuf<double> K(ctx, (size_t)(nc * d)), K1(ctx, (size_t)(nc * d));
+    whitening_kernel<<<(unsigned)ceil_div(nc * d, 256), 256, 0, ctx->stream>>>(Jt.p, lam.p, nc, d, 1.0, K.p);
+    launch1(ctx);
+    whitening_kernel<<<(unsigned)ceil_div(nc * d, 256), 256, 0, ctx->stream>>>(Jt.p, lam.p, nc, d,
+                                                                              std::sqrt((double)n_total), K1.p);
+    launch1(ctx);
+
+    DBuf<double> Wd(ctx, (size_t)(nc * nc)), Winit_d(ctx, (size_t)(nc * nc));
+    launch_cast<T, double>(ctx, Winit.p, Winit_d.p, nc * nc);
+    int64_t iters = 0;
+    double lim = 0.0;
+    ica_par<T>(ctx, X.p, n, d, n_total, cm.mu, K1.p, nc, fun, tol, max_iter, lim_variant, Winit_d.p, Wd.p, &iters, &lim);
+
+    // components = W K (src/ica.rs:217)
+    DBuf<double> Cd(ctx, (size_t)(nc * d));
+    gemm_xb<double>(ctx, Wd.p, nc, nc, nc, K.p, d, false, d, nullptr, nullptr, Cd.p, d);
+    DBuf<T> comps_tmp;
+    T* comps_dev = comps.p;
+    if (!comps_dev) {
+        comps_tmp.alloc(ctx, (size_t)(nc * d));
+        comps_dev = comps_tmp.p;
+    }
+    launch_cast<double, T>(ctx, Cd.p, comps_dev, nc * d);
+    if (sources)  // fit_transform = (components * xc)^T (src/ica.rs:155-156)
+        gemm_xb<T>(ctx, X.p, d, n, d, comps_dev, d, true, nc, cm.mu, nullptr, sources.p, nc);
+    if (mean) launch_cast<T, T>(ctx, cm.mean_t.p, mean.p, d);
+    if (n_iter_u) *n_iter_u = iters;
+    if (lim_u) *lim_u = lim;
+    comps.commit(ctx); mean.commit(ctx); sources.commit(ctx);
+    finish_call(ctx, comps.to_host || mean.to_host || sources.to_host);
+}
+
+}  // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int petal_ctx_create(int device, petal_ctx** out) {
+    if (!out) return PETAL_INVALID_INPUT;
+    *out = nullptr;
+    try {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error{PETAL_LINALG_ERROR, std::string("no CUDA device available (libpetal_b200 has no CPU fallback): ") +
+                                                cudaGetErrorString(e)};
+        if (device < 0 || device >= count) throw Error{PETAL_INVALID_INPUT, "invalid device ordinal"};
+        PETAL_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        PETAL_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw Error{PETAL_LINALG_ERROR, std::string("libpetal_b200 is built for sm_100a only; device is sm_") +
+                                                std::to_string(prop.major) + std::to_string(prop.minor)};
+        petal_ctx* ctx = new petal_ctx;
+        ctx->device = device;
+        ctx->sm_count = prop.multiProcessorCount;
+        PETAL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thresh = (uint64_t)8 << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+        }
+        *out = ctx;
+        return PETAL_OK;
+    } catch (const Error& e) {
+        std::lock_guard<std::mutex> lk(g_global_mutex);
+        g_global_error = e.msg;
+        cudaGetLastError();
+        return e.code;
+    }
+}
+
+void petal_ctx_destroy(petal_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->comm;
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* petal_last_error(const petal_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char* petal_last_global_error(void) { return g_global_error.c_str(); }
+
+int petal_ctx_set_stream(petal_ctx* ctx, void* cuda_stream) {
+    return guarded(ctx, [&] {
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+        ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+        ctx->own_stream = false;
+    });
+}
+
+int petal_ctx_synchronize(petal_ctx* ctx) {
+    return guarded(ctx, [&] { PETAL_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+
+int64_t petal_ctx_launch_count(const petal_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int petal_ctx_set_f32_engine(petal_ctx* ctx, int engine) {
+    if (!ctx) return -1;
+    if (engine >= 0) ctx->f32_engine = engine ? 1 : 0;
+    return ctx->f32_engine;
+}
+
+int petal_ctx_set_profiling(petal_ctx* ctx, int enable) {
+    if (!ctx) return PETAL_INVALID_INPUT;
+    ctx->profiling = enable != 0;
+    return PETAL_OK;
+}
+
+// JSON: {"kernel": {"count": c, "total_ms": t, "min_ms": a, "max_ms": b, "work": w}, ...}; clears the log.
+int64_t petal_ctx_profile_json(petal_ctx* ctx, char* buf, int64_t cap) {
+    if (!ctx) return -1;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    struct Agg { const char* name; int64_t count; double total, mn, mx, work; };
+    std::vector<Agg> aggs;
+    for (auto& e : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+        Agg* a = nullptr;
+        for (auto& x : aggs) if (std::strcmp(x.name, e.name) == 0) a = &x;
+        if (!a) { aggs.push_back(Agg{e.name, 0, 0.0, 1e30, 0.0, 0.0}); a = &aggs.back(); }
+        a->count++; a->total += ms; a->mn = std::min(a->mn, (double)ms); a->mx = std::max(a->mx, (double)ms);
+        a->work += e.work;
+    }
+    ctx->prof.clear();
+    std::string out = "{";
+    for (size_t i = 0; i < aggs.size(); ++i) {
+        char tmp[512];
+        std::snprintf(tmp, sizeof tmp, "%s\"%s\": {\"count\": %lld, \"total_ms\": %.6f, \"min_ms\": %.6f, \"max_ms\": %.6f, \"work\": %.1f}",
+                      i ? ", " : "", aggs[i].name, (long long)aggs[i].count, aggs[i].total, aggs[i].mn, aggs[i].mx, aggs[i].work);
+        out += tmp;
+    }
+    out += "}";
+    if (buf && cap > 0) {
+        std::strncpy(buf, out.c_str(), (size_t)cap - 1);
+        buf[cap - 1] = 0;
+    }
+    return (int64_t)out.size() + 1;
+}
+
+int petal_comm_unique_id(void* out_id) {
+    try {
+        ncclUniqueId id;
+        PETAL_NCCL(nccl_api().GetUniqueId(&id));
+        std::memcpy(out_id, &id, sizeof id);
+        return PETAL_OK;
+    } catch (const Error& e) {
+        std::lock_guard<std::mutex> lk(g_global_mutex);
+        g_global_error = e.msg;
+        return e.code;
+    }
+}
+
+int petal_comm_init(petal_ctx* ctx, const void* id, int rank, int world_size) {
+    return guarded(ctx, [&] {
+        if (world_size < 1 || rank < 0 || rank >= world_size) invalid_input("invalid rank / world size");
+        delete ctx->comm;
+        ctx->comm = nullptr;
+        ctx->rank = rank;
+        ctx->world = world_size;
+        if (world_size == 1) return;
+        ncclUniqueId uid;
+        std::memcpy(&uid, id, sizeof uid);
+        Comm* c = new Comm;
+        ncclResult_t r = nccl_api().CommInitRank(&c->comm, world_size, uid, rank);
+        if (r != ncclSuccess) {
+            delete c;
+            ctx->world = 1;
+            linalg_error(std::string("ncclCommInitRank failed: ") + nccl_api().GetErrorString(r));
+        }
+        ctx->comm = c;
+    });
+}
+
+#define PETAL_DEFINE_TYPED(SUFFIX, T)                                                                          \
+    int petal_pca_fit_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, int64_t k, int centering,      \
+                               T* components, T* mean, T* singular, T* total_variance, T* scores) {            \
+        return guarded(ctx, [&] {                                                                              \
+            pca_fit<T>(ctx, x, n, d, k, centering != 0, components, mean, singular, total_variance, scores);   \
+        });                                                                                                    \
+    }                                                                                                          \
+    int petal_rpca_fit_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, int64_t k, int centering,     \
+                                int64_t n_oversamples, int64_t n_power_iter, const T* omega, T* components,    \
+                                T* mean, T* singular, T* total_variance, T* scores) {                          \
+        return guarded(ctx, [&] {                                                                              \
+            rpca_fit<T>(ctx, x, n, d, k, centering != 0, n_oversamples, n_power_iter, omega, components, mean, \
+                        singular, total_variance, scores);                                                     \
+        });                                                                                                    \
+    }                                                                                                          \
+    int petal_transform_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, const T* components,         \
+                                 int64_t k, const T* mean, T* out) {                                           \
+        return guarded(ctx, [&] { transform<T>(ctx, x, n, d, components, k, mean, out); });                    \
+    }                                                                                                          \
+    int petal_inverse_transform_##SUFFIX(petal_ctx* ctx, const T* y, int64_t n, int64_t k,                      \
+                                         const T* components, int64_t d, const T* mean, T* out) {              \
+        return guarded(ctx, [&] { inverse_transform<T>(ctx, y, n, k, components, d, mean, out); });            \
+    }                                                                                                          \
+    int petal_fastica_fit_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, int fun, double tol,       \
+                                   int64_t max_iter, int lim_variant, const T* w_init, T* components, T* mean, \
+                                   int64_t* n_iter, double* final_lim, T* sources) {                           \
+        return guarded(ctx, [&] {                                                                              \
+            fastica_fit<T>(ctx, x, n, d, fun, tol, max_iter, lim_variant, w_init, components, mean, n_iter,    \
+                           final_lim, sources);                                                                \
+        });                                                                                                    \
+    }                                                                                                          \
+    int petal_colmean_gram_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, int centering,            \
+                                    double* mean, double* gram) {                                              \
+        return guarded(ctx, [&] {                                                                              \
+            const int64_t n_total = global_rows(ctx, n);                                                       \
+            DevIn<T> X(ctx, x, (size_t)(n * d));                                                               \
+            DevOut<double> m(ctx, mean, (size_t)d), g(ctx, gram, (size_t)(d * d));                             \
+            if (n_total == 0 || d == 0) return;                                                                \
+            ColMean<T> cm;                                                                                     \
+            compute_mean<T>(ctx, X.p, n, d, n_total, centering != 0, cm);                                      \
+            if (g) centered_gram<T>(ctx, X.p, n, d, d, cm.mu, g.p);                                            \
+            if (m) launch_cast<double, double>(ctx, cm.mean_d.p, m.p, d);                                      \
+            m.commit(ctx);                                                                                     \
+            g.commit(ctx);                                                                                     \
+            finish_call(ctx, m.to_host || g.to_host);                                                          \
+        });                                                                                                    \
+    }
+
+PETAL_DEFINE_TYPED(f32, float)
+PETAL_DEFINE_TYPED(f64, double)
+
+int petal_ica_par_f64(petal_ctx* ctx, const double* x1t, int64_t n, int64_t nc, int fun, double tol,
+                      int64_t max_iter, int lim_variant, const double* w_init, double* w_out, int64_t* n_iter,
+                      double* final_lim) {
+    return guarded(ctx, [&] {
+        if (n <= 0 || nc <= 0) invalid_input("empty input");
+        const int64_t n_total = global_rows(ctx, n);
+        DevIn<double> X(ctx, x1t, (size_t)(n * nc)), Wi(ctx, w_init, (size_t)(nc * nc));
+        DevOut<double> W(ctx, w_out, (size_t)(nc * nc));
+        if (!W) invalid_input("output buffer is null");
+        int64_t iters = 0;
+        double lim = 0.0;
+        ica_par<double>(ctx, X.p, n, nc, n_total, nullptr, nullptr, nc, fun, tol, max_iter, lim_variant, Wi.p, W.p,
+                        &iters, &lim);
+        if (n_iter) *n_iter = iters;
+        if (final_lim) *final_lim = lim;
+        W.commit(ctx);
+        finish_call(ctx, W.to_host);
+    });
+}
+
+int petal_symmetric_decorrelation_f64(petal_ctx* ctx, const double* w, int64_t m, double* out) {
+    return guarded(ctx, [&] {
+        if (m <= 0) invalid_input("empty input");
+        DevIn<double> W(ctx, w, (size_t)(m * m));
+        DevOut<double> O(ctx, out, (size_t)(m * m));
+        if (!O) invalid_input("output buffer is null");
+        symmetric_decorrelation(ctx, W.p, m, O.p);
+        O.commit(ctx);
+        finish_call(ctx, O.to_host);
+    });
+}
+
+int petal_small_svd_f64(petal_ctx* ctx, const double* a, int64_t m, int64_t len, double* u, double* s, double* vt) {
+    return guarded(ctx, [&] {
+        if (m <= 0 || len <= 0) invalid_input("empty input");
+        DevIn<double> A(ctx, a, (size_t)(m * len));
+        DevOut<double> U(ctx, u, (size_t)(m * m)), S(ctx, s, (size_t)m), Vt(ctx, vt, (size_t)(m * len));
+        DBuf<double> Aout(ctx, (size_t)(m * len)), Jt(ctx, (size_t)(m * m)), sig(ctx, (size_t)m);
+        jacobi_rows(ctx, A.p, m, len, Aout.p, Jt.p, sig.p);
+        if (Vt) launch_normalize_rows(ctx, Aout.p, sig.p, m, len, 0.0, Vt.p);
+        if (U) launch_transpose(ctx, Jt.p, m, m, U.p);
+        if (S) launch_cast<double, double>(ctx, sig.p, S.p, m);
+        U.commit(ctx);
+        S.commit(ctx);
+        Vt.commit(ctx);
+        finish_call(ctx, U.to_host || S.to_host || Vt.to_host);
+    });
+}
+
+}  // extern "C"

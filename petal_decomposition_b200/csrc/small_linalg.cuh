@@ -1,0 +1,350 @@
+// Small replicated dense factorizations on device, all f64: a one-sided (Hestenes) Jacobi SVD.
+//
+// It replaces every LAPACK call the reference makes (src/linalg/lapack.rs: gesvd :103-132,
+// gesdd :70-101, syev/heev :134-184, gelqf/orglq :49-68,186-202) on the small matrices that
+// are replicated on every GPU: the d x d Gram of exact PCA / whitening, the l x l Grams of the
+// range finder, the l x d projected matrix B and the nc x nc FastICA update.
+//
+// Formulation ("rows"): given m vectors of length len (row-major A[m][len]) find an orthogonal
+// Jt[m][m] such that Jt * A has mutually orthogonal rows:  Jt * A = diag(s) * N,  N N^T = I.
+//   -> SVD            A = U diag(s) Vt   with U = Jt^T, Vt = N
+//   -> eigh (A sym. PSD): eigenvalues s, eigenvectors = rows of Jt
+//   -> polar factor   (A A^T)^-1/2 A = Jt^T N                      (symmetric decorrelation)
+// Rows are returned sorted by s descending.
+//
+// Two engines: one CTA with everything in shared memory (m*(len+m)*8 B <= 200 KB; latency-bound
+// problems such as the 64 x 64 FastICA update), and a multi-CTA engine working in global memory
+// (L2-resident for moderate sizes) with one launch per round-robin step.
+#pragma once
+#include "common.cuh"
+
+namespace petal {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// round-robin (circle method) pairing: step s in [0, me-1), pair index i in [0, me/2)
+__device__ __forceinline__ void rr_pair(int me, int s, int i, int& p, int& q) {
+    const int r = me - 1;
+    if (i == 0) {
+        p = r;
+        q = s;
+    } else {
+        p = (s + i) % r;
+        q = (s - i + r) % r;
+    }
+    if (p > q) {
+        int t = p;
+        p = q;
+        q = t;
+    }
+}
+
+// Computes the rotation for a row pair; returns false when already orthogonal to tolerance.
+__device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol,
+                                                double& c, double& s) {
+    if (!(fabs(gamma) > tol * sqrt(alpha) * sqrt(beta))) return false;  // also false for NaN/zero rows
+    double zeta = (beta - alpha) / (2.0 * gamma);
+    double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    c = rsqrt(1.0 + t * t);
+    s = c * t;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// single-CTA engine
+// ------------------------------------------------------------------------------------------
+constexpr int kJacobiSmemThreads = 512;
+
+__global__ void __launch_bounds__(kJacobiSmemThreads)
+jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restrict__ Aout,
+                   double* __restrict__ Jt, double* __restrict__ sig, int max_sweeps, double tol,
+                   int* __restrict__ info) {
+    extern __shared__ double sm[];
+    double* M = sm;                       // m x len
+    double* J = sm + (size_t)m * len;     // m x m
+    double* nrm = J + (size_t)m * m;      // m
+    __shared__ int rotated;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = kJacobiSmemThreads / 32;
+
+    for (int i = tid; i < m * len; i += kJacobiSmemThreads) M[i] = A[i];
+    for (int i = tid; i < m * m; i += kJacobiSmemThreads) J[i] = ((i / m) == (i % m)) ? 1.0 : 0.0;
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+
+    const int me = (m + 1) & ~1;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
+        for (int step = 0; step < me - 1; ++step) {
+            for (int pi = warp; pi < me / 2; pi += nwarps) {
+                int p, q;
+                rr_pair(me, step, pi, p, q);
+                if (q >= m) continue;
+                double* mp = M + (size_t)p * len;
+                double* mq = M + (size_t)q * len;
+                double al = 0.0, be = 0.0, ga = 0.0;
+                for (int e = lane; e < len; e += 32) {
+                    double x = mp[e], y = mq[e];
+                    al += x * x;
+                    be += y * y;
+                    ga += x * y;
+                }
+                al = warp_sum(al);
+                be = warp_sum(be);
+                ga = warp_sum(ga);
+                double c, s;
+                if (!jacobi_rotation(al, be, ga, tol, c, s)) continue;
+                for (int e = lane; e < len; e += 32) {
+                    double x = mp[e], y = mq[e];
+                    mp[e] = c * x - s * y;
+                    mq[e] = s * x + c * y;
+                }
+                double* jp = J + (size_t)p * m;
+                double* jq = J + (size_t)q * m;
+                for (int e = lane; e < m; e += 32) {
+                    double x = jp[e], y = jq[e];
+                    jp[e] = c * x - s * y;
+                    jq[e] = s * x + c * y;
+                }
+                if (lane == 0) rotated = 1;
+            }
+            __syncthreads();
+        }
+        sweeps = sweep + 1;
+        int r = rotated;
+        __syncthreads();
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        if (!r) break;
+    }
+
+    // norms
+    for (int j = warp; j < m; j += nwarps) {
+        double a = 0.0;
+        for (int e = lane; e < len; e += 32) a += M[(size_t)j * len + e] * M[(size_t)j * len + e];
+        a = warp_sum(a);
+        if (lane == 0) nrm[j] = sqrt(a);
+    }
+    __syncthreads();
+    // rank sort (descending, stable) and scatter
+    for (int j = warp; j < m; j += nwarps) {
+        double sj = nrm[j];
+        int rank = 0;
+        for (int i = lane; i < m; i += 32) {
+            double si = nrm[i];
+            rank += (si > sj || (si == sj && i < j)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (lane == 0) sig[rank] = sj;
+        if (Aout)
+            for (int e = lane; e < len; e += 32) Aout[(size_t)rank * len + e] = M[(size_t)j * len + e];
+        if (Jt)
+            for (int e = lane; e < m; e += 32) Jt[(size_t)rank * m + e] = J[(size_t)j * m + e];
+    }
+    if (tid == 0 && info) *info = sweeps;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-CTA engine (global memory)
+// ------------------------------------------------------------------------------------------
+__global__ void set_identity_kernel(double* J, int64_t m) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m * m) J[i] = ((i / m) == (i % m)) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+jacobi_step_kernel(double* __restrict__ M, int m, int len, double* __restrict__ J, int me, int step,
+                   double tol, int* __restrict__ rotated) {
+    int p, q;
+    rr_pair(me, step, blockIdx.x, p, q);
+    if (q >= m) return;
+    double* mp = M + (size_t)p * len;
+    double* mq = M + (size_t)q * len;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double al = 0.0, be = 0.0, ga = 0.0;
+    for (int e = tid; e < len; e += 256) {
+        double x = mp[e], y = mq[e];
+        al += x * x;
+        be += y * y;
+        ga += x * y;
+    }
+    __shared__ double red[3][8];
+    al = warp_sum(al);
+    be = warp_sum(be);
+    ga = warp_sum(ga);
+    if (lane == 0) {
+        red[0][warp] = al;
+        red[1][warp] = be;
+        red[2][warp] = ga;
+    }
+    __syncthreads();
+    al = be = ga = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        al += red[0][w];
+        be += red[1][w];
+        ga += red[2][w];
+    }
+    double c, s;
+    if (!jacobi_rotation(al, be, ga, tol, c, s)) return;
+    for (int e = tid; e < len; e += 256) {
+        double x = mp[e], y = mq[e];
+        mp[e] = c * x - s * y;
+        mq[e] = s * x + c * y;
+    }
+    double* jp = J + (size_t)p * m;
+    double* jq = J + (size_t)q * m;
+    for (int e = tid; e < m; e += 256) {
+        double x = jp[e], y = jq[e];
+        jp[e] = c * x - s * y;
+        jq[e] = s * x + c * y;
+    }
+    if (tid == 0) *rotated = 1;
+}
+
+__global__ void __launch_bounds__(256)
+row_norm_kernel(const double* __restrict__ M, int m, int len, double* __restrict__ nrm) {
+    const int j = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a = 0.0;
+    for (int e = tid; e < len; e += 256) {
+        double x = M[(size_t)j * len + e];
+        a += x * x;
+    }
+    __shared__ double red[8];
+    a = warp_sum(a);
+    if (lane == 0) red[warp] = a;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        nrm[j] = sqrt(s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sort_scatter_kernel(const double* __restrict__ M, const double* __restrict__ J,
+                    const double* __restrict__ nrm, int m, int len, double* __restrict__ Aout,
+                    double* __restrict__ Jt, double* __restrict__ sig) {
+    const int j = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ int rank_s;
+    if (tid == 0) rank_s = 0;
+    __syncthreads();
+    double sj = nrm[j];
+    int rank = 0;
+    for (int i = tid; i < m; i += 256) {
+        double si = nrm[i];
+        rank += (si > sj || (si == sj && i < j)) ? 1 : 0;
+    }
+    if (rank) atomicAdd(&rank_s, rank);
+    __syncthreads();
+    rank = rank_s;
+    if (tid == 0) sig[rank] = sj;
+    if (Aout)
+        for (int e = tid; e < len; e += 256) Aout[(size_t)rank * len + e] = M[(size_t)j * len + e];
+    if (Jt)
+        for (int e = tid; e < m; e += 256) Jt[(size_t)rank * m + e] = J[(size_t)j * m + e];
+}
+
+// A[m][len] (device, f64, not modified) -> Aout[m][len] (= diag(sig) N, may be null),
+// Jt[m][m] (may be null), sig[m].  Returns the number of sweeps used (-1 if unknown).
+inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, double* Aout, double* Jt,
+                       double* sig, bool force_global = false) {
+    if (m == 0) return 0;
+    if (m > (int64_t)1 << 20 || len > (int64_t)1 << 30) invalid_input("matrix too large for the Jacobi solver");
+    const int max_sweeps = 60;
+    const double tol = 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
+    size_t smem = ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double);
+    KTimer kt(ctx, "jacobi", 0.0);
+    if (!force_global && smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            PETAL_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            200 * 1024));
+            attr_set = true;
+        }
+        jacobi_smem_kernel<<<1, kJacobiSmemThreads, smem, ctx->stream>>>(A, (int)m, (int)len, Aout, Jt, sig,
+                                                                         max_sweeps, tol, nullptr);
+        check_launch(ctx);
+        return -1;
+    }
+    DBuf<double> M(ctx, (size_t)(m * len));
+    DBuf<double> J(ctx, (size_t)(m * m));
+    DBuf<double> nrm(ctx, (size_t)m);
+    DBuf<int> rotated(ctx, 1);
+    PETAL_CUDA(cudaMemcpyAsync(M.p, A, (size_t)(m * len) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    set_identity_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, ctx->stream>>>(J.p, m);
+    check_launch(ctx);
+    const int me = (int)((m + 1) & ~(int64_t)1);
+    int sweeps = 0;
+    for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
+        rotated.zero();
+        for (int step = 0; step < me - 1; ++step) {
+            jacobi_step_kernel<<<me / 2, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, J.p, me, step, tol,
+                                                                rotated.p);
+            check_launch(ctx);
+        }
+        int h = 0;
+        PETAL_CUDA(cudaMemcpyAsync(&h, rotated.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        sweeps = sweep + 1;
+        if (!h) break;
+    }
+    row_norm_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, nrm.p);
+    check_launch(ctx);
+    sort_scatter_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, J.p, nrm.p, (int)m, (int)len, Aout, Jt, sig);
+    check_launch(ctx);
+    return sweeps;
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers built on the factorization
+// ------------------------------------------------------------------------------------------
+// N[j][:] = Aout[j][:] / sig[j]  (zero row when sig[j] <= cutoff * sig[0])
+__global__ void normalize_rows_kernel(const double* __restrict__ Aout, const double* __restrict__ sig,
+                                      int64_t m, int64_t len, double cutoff, double* __restrict__ N) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * len) return;
+    int64_t j = idx / len;
+    double s = sig[j];
+    double s0 = sig[0];
+    N[idx] = (s > cutoff * s0 && s > 0.0) ? Aout[idx] / s : 0.0;
+}
+
+inline void launch_normalize_rows(petal_ctx* ctx, const double* Aout, const double* sig, int64_t m,
+                                  int64_t len, double cutoff, double* N) {
+    if (m * len == 0) return;
+    normalize_rows_kernel<<<(unsigned)ceil_div(m * len, 256), 256, 0, ctx->stream>>>(Aout, sig, m, len, cutoff, N);
+    check_launch(ctx);
+}
+
+// P[a][j] = Jt[j][a] * f(sig[j]),   mode 0: f = 1/sqrt(s)  (s = eigenvalue of a Gram matrix)
+//                                    mode 1: f = 1/s
+//                                    mode 2: f = 1
+// f = 0 when s <= cutoff * s[0]  (rank-deficient directions are dropped, not amplified)
+__global__ void scaled_transpose_kernel(const double* __restrict__ Jt, const double* __restrict__ sig,
+                                        int64_t m, int mode, double cutoff, double* __restrict__ P) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * m) return;
+    int64_t a = idx / m, j = idx % m;
+    double s = sig[j], s0 = sig[0];
+    double f = 0.0;
+    if (mode == 2) f = 1.0;
+    else if (s > cutoff * s0 && s > 0.0) f = (mode == 0) ? rsqrt(s) : 1.0 / s;
+    P[idx] = Jt[j * m + a] * f;
+}
+
+inline void launch_scaled_transpose(petal_ctx* ctx, const double* Jt, const double* sig, int64_t m, int mode,
+                                    double cutoff, double* P) {
+    if (m == 0) return;
+    scaled_transpose_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, ctx->stream>>>(Jt, sig, m, mode, cutoff, P);
+    check_launch(ctx);
+}
+
+}  // namespace petal

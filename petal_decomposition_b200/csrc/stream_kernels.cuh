@@ -1,0 +1,739 @@
+// Streaming (row-sharded, HBM-bound) kernels of the fit/transform hot path - SIMT engine.
+//
+//   colsum   : column sums                      (reference: mean_axis, src/pca.rs:207,521; src/ica.rs:174)
+//   xb       : Y = (A - mu) * B + bias          (X*Omega, X*P, transform, inverse_transform;
+//                                                src/pca.rs:707,714,745,806; src/ica.rs:130,332)
+//   atb      : C += (A - mua)^T (B - mub)       (Gram / X^T*Q / Q^T*X; src/pca.rs:681,711; src/ica.rs:333)
+//   nonlin   : g(u), sum g'(u)                  (logcosh, src/ica.rs:383-398; exp / cube extensions)
+//   colabsmax: per column (max |.|, first row, sign)   (svd_flip, src/pca.rs:815-850)
+//
+// The centred copy of X that the reference materialises (src/pca.rs:217,531; src/ica.rs:178-188)
+// never exists here: `mu` is subtracted while a tile is staged into shared memory.
+// All kernels take row-major inputs with explicit leading dimensions, are fully bounds-guarded
+// (ragged / tiny shapes), use 128-bit loads when the layout allows (ALIGNED), and reduce across
+// CTAs with f64 atomics.
+#pragma once
+#include "common.cuh"
+
+namespace petal {
+
+// ------------------------------------------------------------------------------------------
+// colsum
+// ------------------------------------------------------------------------------------------
+template <typename T, bool VECLOAD>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ X, int64_t n, int64_t d, int64_t ld, double* __restrict__ sum,
+              int tx, int64_t rows_per_cta) {
+    constexpr int V = VECLOAD ? Pack<T>::N : 1;
+    const int ty = 256 / tx;
+    const int cx = threadIdx.x % tx;
+    const int ry = threadIdx.x / tx;
+    const int64_t col0 = ((int64_t)blockIdx.x * tx + cx) * V;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(n, r0 + rows_per_cta);
+    double acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.0;
+    if (col0 < d) {
+        const T* base = X + col0;
+        int64_t r = r0 + ry;
+        if constexpr (VECLOAD) {
+            for (; r + 3 * (int64_t)ty < r1; r += 4 * (int64_t)ty) {
+                Pack<T> a0 = *reinterpret_cast<const Pack<T>*>(base + r * ld);
+                Pack<T> a1 = *reinterpret_cast<const Pack<T>*>(base + (r + ty) * ld);
+                Pack<T> a2 = *reinterpret_cast<const Pack<T>*>(base + (r + 2 * ty) * ld);
+                Pack<T> a3 = *reinterpret_cast<const Pack<T>*>(base + (r + 3 * ty) * ld);
+#pragma unroll
+                for (int v = 0; v < V; ++v)
+                    acc[v] += ((double)a0.v[v] + (double)a1.v[v]) + ((double)a2.v[v] + (double)a3.v[v]);
+            }
+            for (; r < r1; r += ty) {
+                Pack<T> a0 = *reinterpret_cast<const Pack<T>*>(base + r * ld);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] += (double)a0.v[v];
+            }
+        } else {
+            for (; r + 3 * (int64_t)ty < r1; r += 4 * (int64_t)ty) {
+                T a0 = base[r * ld], a1 = base[(r + ty) * ld], a2 = base[(r + 2 * ty) * ld],
+                  a3 = base[(r + 3 * ty) * ld];
+                acc[0] += ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+            }
+            for (; r < r1; r += ty) acc[0] += (double)base[r * ld];
+        }
+    }
+    __shared__ double red[256 * 4];
+#pragma unroll
+    for (int v = 0; v < V; ++v) red[(ry * tx + cx) * V + v] = acc[v];
+    __syncthreads();
+    if (ry == 0 && col0 < d) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            double s = 0.0;
+            for (int y = 0; y < ty; ++y) s += red[(y * tx + cx) * V + v];
+            atomicAdd(&sum[col0 + v], s);
+        }
+    }
+}
+
+inline int pow2_ceil(int64_t x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// sum[d] (f64) += column sums of X. `sum` must be zeroed by the caller.
+template <typename T>
+void launch_colsum(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, double* sum) {
+    if (n == 0 || d == 0) return;
+    constexpr int V = Pack<T>::N;
+    bool vec = (d % V == 0) && (ld % V == 0) && is_aligned16(X);
+    int64_t cols = vec ? d / V : d;
+    int tx = (int)std::min<int64_t>(256, pow2_ceil(cols));
+    int ty = 256 / tx;
+    int64_t gx = ceil_div(cols, tx);
+    int64_t target_ctas = (int64_t)ctx->sm_count * 8;
+    int64_t gy = std::max<int64_t>(1, std::min<int64_t>(target_ctas / gx, ceil_div(n, (int64_t)ty * 8)));
+    gy = std::min<int64_t>(gy, 65535);
+    int64_t rows_per_cta = ceil_div(n, gy);
+    gy = ceil_div(n, rows_per_cta);
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    KTimer kt(ctx, kname<T>("colsum_f32", "colsum_f64"), (double)n * d * sizeof(T));
+    if (vec)
+        colsum_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(X, n, d, ld, sum, tx, rows_per_cta);
+    else
+        colsum_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(X, n, d, ld, sum, tx, rows_per_cta);
+    check_launch(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// xb : Y[n x L] = (A[n x K] - mu) * B + bias        (B is K x L row-major, or L x K if b_trans)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct XbParams {
+    const T* A;
+    int64_t lda;
+    int64_t n;
+    int64_t K;
+    const T* B;
+    int64_t ldb;
+    int b_trans;
+    int64_t L;
+    const T* mu;    // nullable [K]
+    const T* bias;  // nullable [L]
+    T* Y;
+    int64_t ldy;
+    double* sumsq;  // nullable: += sum((A - mu)^2)
+};
+
+template <typename T, int TN, bool ALIGNED>
+__global__ void __launch_bounds__(256) xb_kernel(XbParams<T> p) {
+    constexpr int V = Pack<T>::N;
+    constexpr int BM = 128, TM = 8, BN = 16 * TN, BK = 8 * V;
+    constexpr int LDS_A = BK + V;
+    constexpr int A_VECS = BM * BK / V / 256;  // 4
+    constexpr int B_ELEMS = (BK * BN + 255) / 256;
+    __shared__ __align__(16) T As[BM * LDS_A];
+    __shared__ __align__(16) T Bs[BK * BN];
+    __shared__ double red[8];
+
+    const int tid = threadIdx.x;
+    const int tr = tid >> 4, tc = tid & 15;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int64_t col0 = (int64_t)blockIdx.y * BN;
+    const bool want_ss = (p.sumsq != nullptr) && (blockIdx.y == 0);
+
+    T acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+    Pack<T> a_stage[A_VECS];
+    T b_stage[B_ELEMS];
+    double ss = 0.0;
+
+    auto load_tiles = [&](int64_t k0) {
+#pragma unroll
+        for (int i = 0; i < A_VECS; ++i) {
+            int idx = tid + i * 256;
+            int m = idx >> 3;  // BK / V == 8 vectors per row
+            int kv = idx & 7;
+            int64_t r = row0 + m;
+            int64_t kk = k0 + kv * V;
+            Pack<T> z;
+#pragma unroll
+            for (int v = 0; v < V; ++v) z.v[v] = T(0);
+            if (r < p.n && kk < p.K) {
+                if constexpr (ALIGNED) {
+                    z = *reinterpret_cast<const Pack<T>*>(p.A + r * p.lda + kk);
+                    if (p.mu) {
+                        Pack<T> m4 = *reinterpret_cast<const Pack<T>*>(p.mu + kk);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) z.v[v] -= m4.v[v];
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (kk + v < p.K) {
+                            T x = p.A[r * p.lda + kk + v];
+                            if (p.mu) x -= p.mu[kk + v];
+                            z.v[v] = x;
+                        }
+                }
+                if (want_ss) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) ss += (double)z.v[v] * (double)z.v[v];
+                }
+            }
+            a_stage[i] = z;
+        }
+#pragma unroll
+        for (int i = 0; i < B_ELEMS; ++i) {
+            int idx = tid + i * 256;
+            T val = T(0);
+            if (idx < BK * BN) {
+                int kk = idx / BN, c = idx % BN;
+                int64_t gk = k0 + kk, gc = col0 + c;
+                if (gk < p.K && gc < p.L) val = p.b_trans ? p.B[gc * p.ldb + gk] : p.B[gk * p.ldb + gc];
+            }
+            b_stage[i] = val;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int i = 0; i < A_VECS; ++i) {
+            int idx = tid + i * 256;
+            int m = idx >> 3, kv = idx & 7;
+            *reinterpret_cast<Pack<T>*>(&As[m * LDS_A + kv * V]) = a_stage[i];
+        }
+#pragma unroll
+        for (int i = 0; i < B_ELEMS; ++i) {
+            int idx = tid + i * 256;
+            if (idx < BK * BN) Bs[idx] = b_stage[i];
+        }
+    };
+
+    load_tiles(0);
+    store_tiles();
+    __syncthreads();
+    for (int64_t k0 = 0; k0 < p.K; k0 += BK) {
+        const bool has_next = (k0 + BK) < p.K;
+        if (has_next) load_tiles(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += V) {
+            Pack<T> a[TM];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+                a[i] = *reinterpret_cast<const Pack<T>*>(&As[(tr * TM + i) * LDS_A + kk]);
+            T b[V][TN];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[v][j] = Bs[(kk + v) * BN + tc + 16 * j];
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] += a[i].v[v] * b[v][j];
+        }
+        __syncthreads();
+        if (has_next) {
+            store_tiles();
+            __syncthreads();
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int64_t r = row0 + tr * TM + i;
+        if (r >= p.n) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int64_t c = col0 + tc + 16 * j;
+            if (c < p.L) {
+                T v = acc[i][j];
+                if (p.bias) v += p.bias[c];
+                p.Y[r * p.ldy + c] = v;
+            }
+        }
+    }
+    if (want_ss) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((tid & 31) == 0) red[tid >> 5] = ss;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            atomicAdd(p.sumsq, s);
+        }
+    }
+}
+
+template <typename T, int TN>
+void launch_xb_tn(petal_ctx* ctx, const XbParams<T>& p, bool aligned) {
+    dim3 grid((unsigned)ceil_div(p.n, 128), (unsigned)ceil_div(p.L, 16 * TN));
+    KTimer kt(ctx, kname<T>("xb_f32", "xb_f64"), (double)p.n * (p.K + p.L) * sizeof(T));
+    if (aligned)
+        xb_kernel<T, TN, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else
+        xb_kernel<T, TN, false><<<grid, 256, 0, ctx->stream>>>(p);
+    check_launch(ctx);
+}
+
+template <typename T>
+void launch_xb(petal_ctx* ctx, const XbParams<T>& p) {
+    if (p.n == 0 || p.L == 0) return;
+    constexpr int V = Pack<T>::N;
+    bool aligned = (p.K % V == 0) && (p.lda % V == 0) && is_aligned16(p.A) &&
+                   (p.mu == nullptr || is_aligned16(p.mu));
+    // smallest column tile that covers L in one pass over A (A is then read exactly once)
+    if (p.L <= 16) launch_xb_tn<T, 1>(ctx, p, aligned);
+    else if (p.L <= 32) launch_xb_tn<T, 2>(ctx, p, aligned);
+    else if (p.L <= 48) launch_xb_tn<T, 3>(ctx, p, aligned);
+    else if (p.L <= 64) launch_xb_tn<T, 4>(ctx, p, aligned);
+    else if (p.L <= 80) launch_xb_tn<T, 5>(ctx, p, aligned);
+    else if (p.L <= 96) launch_xb_tn<T, 6>(ctx, p, aligned);
+    else launch_xb_tn<T, 8>(ctx, p, aligned);
+}
+
+// ------------------------------------------------------------------------------------------
+// atb : C[da x db] (f64) += (A - mua)^T (B - mub), reduction over the n rows, split across CTAs
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct AtbParams {
+    const T* A;
+    int64_t lda;
+    int64_t da;
+    const T* mua;  // nullable
+    const T* B;
+    int64_t ldb;
+    int64_t db;
+    const T* mub;  // nullable
+    int64_t n;
+    int64_t rows_per_cta;
+    double* C;
+    int64_t ldc;
+    int symmetric;  // A == B: compute tiles with tile_j >= tile_i only (mirror afterwards)
+    int tiles_j;
+};
+
+template <typename T, int TI, int TJ, bool ALIGNED>
+__global__ void __launch_bounds__(256) atb_kernel(AtbParams<T> p) {
+    constexpr int V = Pack<T>::N;
+    constexpr int BI = 16 * TI, BJ = 16 * TJ, BR = 16;
+    constexpr bool VEC_I = (TI % V == 0);
+    constexpr bool VEC_J = (TJ % V == 0);
+    constexpr int64_t FLUSH_ROWS = (sizeof(T) == 4) ? 8192 : (int64_t(1) << 62);
+    static_assert(VEC_I, "TI must be a multiple of the vector width");
+    constexpr int A_VECS = BR * BI / V / 256;
+    constexpr int B_ELEMS = BR * BJ / 256;  // == TJ
+    __shared__ __align__(16) T As[BR * BI];
+    __shared__ __align__(16) T Bs[BR * BJ];
+
+    const int tile_i = blockIdx.x / p.tiles_j, tile_j = blockIdx.x % p.tiles_j;
+    if (p.symmetric && tile_j < tile_i) return;
+    const int64_t i0 = (int64_t)tile_i * BI, j0 = (int64_t)tile_j * BJ;
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;
+    const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_cta;
+    const int64_t r_end = min(p.n, r_begin + p.rows_per_cta);
+    if (r_begin >= r_end) return;
+
+    T acc[TI][TJ];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) acc[i][j] = T(0);
+
+    Pack<T> a_stage[A_VECS];
+    T b_stage[B_ELEMS];
+
+    auto load_tiles = [&](int64_t r0) {
+#pragma unroll
+        for (int q = 0; q < A_VECS; ++q) {
+            int idx = tid + q * 256;
+            int rr = idx / (BI / V), cv = idx % (BI / V);
+            int64_t r = r0 + rr, c = i0 + cv * V;
+            Pack<T> z;
+#pragma unroll
+            for (int v = 0; v < V; ++v) z.v[v] = T(0);
+            if (r < r_end && c < p.da) {
+                if constexpr (ALIGNED) {
+                    z = *reinterpret_cast<const Pack<T>*>(p.A + r * p.lda + c);
+                    if (p.mua) {
+                        Pack<T> m4 = *reinterpret_cast<const Pack<T>*>(p.mua + c);
+#pragma unroll
+                        for (int v = 0; v < V; ++v) z.v[v] -= m4.v[v];
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (c + v < p.da) {
+                            T x = p.A[r * p.lda + c + v];
+                            if (p.mua) x -= p.mua[c + v];
+                            z.v[v] = x;
+                        }
+                }
+            }
+            a_stage[q] = z;
+        }
+#pragma unroll
+        for (int q = 0; q < B_ELEMS; ++q) {
+            int idx = tid + q * 256;
+            int rr = idx / BJ, cc = idx % BJ;
+            int64_t r = r0 + rr, c = j0 + cc;
+            T x = T(0);
+            if (r < r_end && c < p.db) {
+                x = p.B[r * p.ldb + c];
+                if (p.mub) x -= p.mub[c];
+            }
+            b_stage[q] = x;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int q = 0; q < A_VECS; ++q) {
+            int idx = tid + q * 256;
+            *reinterpret_cast<Pack<T>*>(&As[idx * V]) = a_stage[q];
+        }
+#pragma unroll
+        for (int q = 0; q < B_ELEMS; ++q) Bs[tid + q * 256] = b_stage[q];
+    };
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < TI; ++i) {
+            int64_t gi = i0 + ti * TI + i;
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) {
+                int64_t gj;
+                if constexpr (VEC_J) gj = j0 + (j / V) * (16 * V) + tj * V + (j % V);
+                else gj = j0 + tj + 16 * j;
+                if (gi < p.da && gj < p.db) atomicAdd(&p.C[gi * p.ldc + gj], (double)acc[i][j]);
+                acc[i][j] = T(0);
+            }
+        }
+    };
+
+    load_tiles(r_begin);
+    store_tiles();
+    __syncthreads();
+    int64_t since_flush = 0;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += BR) {
+        const bool has_next = (r0 + BR) < r_end;
+        if (has_next) load_tiles(r0 + BR);
+#pragma unroll
+        for (int rr = 0; rr < BR; ++rr) {
+            T a[TI], b[TJ];
+#pragma unroll
+            for (int i = 0; i < TI; i += V) {
+                Pack<T> t = *reinterpret_cast<const Pack<T>*>(&As[rr * BI + ti * TI + i]);
+#pragma unroll
+                for (int v = 0; v < V; ++v) a[i + v] = t.v[v];
+            }
+            if constexpr (VEC_J) {
+#pragma unroll
+                for (int j = 0; j < TJ; j += V) {
+                    Pack<T> t = *reinterpret_cast<const Pack<T>*>(&Bs[rr * BJ + (j / V) * (16 * V) + tj * V]);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) b[j + v] = t.v[v];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) b[j] = Bs[rr * BJ + tj + 16 * j];
+            }
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] += a[i] * b[j];
+        }
+        since_flush += BR;
+        if (since_flush >= FLUSH_ROWS) {
+            flush();
+            since_flush = 0;
+        }
+        __syncthreads();
+        if (has_next) {
+            store_tiles();
+            __syncthreads();
+        }
+    }
+    flush();
+}
+
+template <typename T, int TI, int TJ>
+void launch_atb_t(petal_ctx* ctx, AtbParams<T> p, bool aligned) {
+    constexpr int BI = 16 * TI, BJ = 16 * TJ;
+    int64_t tiles_i = ceil_div(p.da, BI), tiles_j = ceil_div(p.db, BJ);
+    p.tiles_j = (int)tiles_j;
+    int64_t tiles = tiles_i * tiles_j;
+    int64_t eff_tiles = p.symmetric ? (tiles_i * (tiles_i + 1)) / 2 : tiles;
+    int64_t target = (int64_t)ctx->sm_count * 4;
+    int64_t gy = std::max<int64_t>(1, target / std::max<int64_t>(1, eff_tiles));
+    gy = std::min<int64_t>(gy, ceil_div(p.n, 64));
+    gy = std::min<int64_t>(std::max<int64_t>(gy, 1), 65535);
+    int64_t rows = ceil_div(ceil_div(p.n, gy), 16) * 16;
+    p.rows_per_cta = rows;
+    gy = ceil_div(p.n, rows);
+    dim3 grid((unsigned)tiles, (unsigned)gy);
+    KTimer kt(ctx, kname<T>("atb_f32", "atb_f64"),
+              (double)p.n * ((p.symmetric ? 0 : p.da) + p.db) * sizeof(T));
+    if (aligned)
+        atb_kernel<T, TI, TJ, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else
+        atb_kernel<T, TI, TJ, false><<<grid, 256, 0, ctx->stream>>>(p);
+    check_launch(ctx);
+}
+
+// C must be zeroed by the caller (the kernel accumulates).
+template <typename T>
+void launch_atb(petal_ctx* ctx, AtbParams<T> p) {
+    if (p.n == 0 || p.da == 0 || p.db == 0) return;
+    constexpr int V = Pack<T>::N;
+    bool aligned = (p.da % V == 0) && (p.lda % V == 0) && is_aligned16(p.A) &&
+                   (p.mua == nullptr || is_aligned16(p.mua));
+    if (p.symmetric) {
+        launch_atb_t<T, 8, 8>(ctx, p, aligned);
+        return;
+    }
+    if (p.db <= 16) launch_atb_t<T, 8, 1>(ctx, p, aligned);
+    else if (p.db <= 32) launch_atb_t<T, 8, 2>(ctx, p, aligned);
+    else if (p.db <= 48) launch_atb_t<T, 8, 3>(ctx, p, aligned);
+    else if (p.db <= 64) launch_atb_t<T, 8, 4>(ctx, p, aligned);
+    else if (p.db <= 80) launch_atb_t<T, 8, 5>(ctx, p, aligned);
+    else if (p.db <= 96) launch_atb_t<T, 8, 6>(ctx, p, aligned);
+    else launch_atb_t<T, 8, 8>(ctx, p, aligned);
+}
+
+__global__ void symmetrize_kernel(double* C, int64_t d, int64_t ldc) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d * d) return;
+    int64_t i = idx / d, j = idx % d;
+    if (i > j) C[i * ldc + j] = C[j * ldc + i];
+}
+
+inline void launch_symmetrize(petal_ctx* ctx, double* C, int64_t d) {
+    if (d == 0) return;
+    symmetrize_kernel<<<(unsigned)ceil_div(d * d, 256), 256, 0, ctx->stream>>>(C, d, d);
+    check_launch(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// nonlin : in place U <- g(U), gsum[c] += sum_r g'(U[r][c])      (FastICA contrast functions)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void ica_g(int fun, T u, T& g, T& gp) {
+    if (fun == PETAL_ICA_LOGCOSH) {
+        g = tanh(u);
+        gp = T(1) - g * g;
+    } else if (fun == PETAL_ICA_EXP) {
+        T e = exp(-u * u * T(0.5));
+        g = u * e;
+        gp = (T(1) - u * u) * e;
+    } else {
+        g = u * u * u;
+        gp = T(3) * u * u;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nonlin_kernel(T* __restrict__ U, int64_t n, int64_t nc, int64_t ld, int fun, double* __restrict__ gsum,
+              int tx, int64_t rows_per_cta) {
+    const int ty = 256 / tx;
+    const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+    const int64_t col = (int64_t)blockIdx.x * tx + cx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(n, r0 + rows_per_cta);
+    double acc = 0.0;
+    if (col < nc) {
+        for (int64_t r = r0 + ry; r < r1; r += ty) {
+            T g, gp;
+            ica_g<T>(fun, U[r * ld + col], g, gp);
+            U[r * ld + col] = g;
+            acc += (double)gp;
+        }
+    }
+    __shared__ double red[256];
+    red[ry * tx + cx] = acc;
+    __syncthreads();
+    if (ry == 0 && col < nc) {
+        double s = 0.0;
+        for (int y = 0; y < ty; ++y) s += red[y * tx + cx];
+        atomicAdd(&gsum[col], s);
+    }
+}
+
+template <typename T>
+void launch_nonlin(petal_ctx* ctx, T* U, int64_t n, int64_t nc, int64_t ld, int fun, double* gsum) {
+    if (n == 0 || nc == 0) return;
+    int tx = (int)std::min<int64_t>(256, pow2_ceil(nc));
+    int ty = 256 / tx;
+    int64_t gx = ceil_div(nc, tx);
+    int64_t gy = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 8 / gx, ceil_div(n, (int64_t)ty * 4)));
+    gy = std::min<int64_t>(gy, 65535);
+    int64_t rows = ceil_div(n, gy);
+    gy = ceil_div(n, rows);
+    KTimer kt(ctx, kname<T>("nonlin_f32", "nonlin_f64"), 2.0 * n * nc * sizeof(T));
+    nonlin_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(U, n, nc, ld, fun, gsum, tx, rows);
+    check_launch(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// colabsmax : per column of S[n x k]: (max |s|, first row attaining it, sign of that entry)
+// ------------------------------------------------------------------------------------------
+struct AbsMax {
+    double a;     // |value|
+    double sgn;   // +1 / -1 (f64::signum semantics: -0.0 -> -1)
+    int64_t idx;  // row index (local)
+};
+
+__device__ __forceinline__ bool absmax_better(const AbsMax& x, const AbsMax& y) {
+    // first maximum wins (reference src/pca.rs:830 `abs <= absmax -> continue`)
+    return x.a > y.a || (x.a == y.a && x.idx < y.idx);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+colabsmax_kernel(const T* __restrict__ S, int64_t n, int64_t k, int64_t ld, AbsMax* __restrict__ partial,
+                 int tx, int64_t rows_per_cta) {
+    const int ty = 256 / tx;
+    const int cx = threadIdx.x % tx, ry = threadIdx.x / tx;
+    const int64_t col = (int64_t)blockIdx.x * tx + cx;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(n, r0 + rows_per_cta);
+    AbsMax best;
+    best.a = -1.0;
+    best.sgn = 1.0;
+    best.idx = INT64_MAX;
+    if (col < k) {
+        for (int64_t r = r0 + ry; r < r1; r += ty) {
+            double v = (double)S[r * ld + col];
+            AbsMax c;
+            c.a = fabs(v);
+            c.sgn = signbit(v) ? -1.0 : 1.0;
+            c.idx = r;
+            if (absmax_better(c, best)) best = c;
+        }
+    }
+    __shared__ AbsMax red[256];
+    red[ry * tx + cx] = best;
+    __syncthreads();
+    if (ry == 0 && col < k) {
+        AbsMax b = red[cx];
+        for (int y = 1; y < ty; ++y) {
+            AbsMax c = red[y * tx + cx];
+            if (absmax_better(c, b)) b = c;
+        }
+        partial[(int64_t)blockIdx.y * k + col] = b;
+    }
+}
+
+// out3[k*3] = (absmax, first local row index, sign) per column
+__global__ void colabsmax_final_kernel(const AbsMax* __restrict__ partial, int64_t chunks, int64_t k,
+                                       double* __restrict__ out3) {
+    int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= k) return;
+    AbsMax b = partial[col];
+    for (int64_t c = 1; c < chunks; ++c) {
+        AbsMax x = partial[c * k + col];
+        if (absmax_better(x, b)) b = x;
+    }
+    if (b.a < 0.0) {  // no rows at all
+        b.a = -1.0;
+        b.sgn = 1.0;
+        b.idx = 0;
+    }
+    out3[col * 3 + 0] = b.a;
+    out3[col * 3 + 1] = (double)b.idx;
+    out3[col * 3 + 2] = b.sgn;
+}
+
+template <typename T>
+void launch_colabsmax(petal_ctx* ctx, const T* S, int64_t n, int64_t k, int64_t ld, double* out3) {
+    if (k == 0) return;
+    int tx = (int)std::min<int64_t>(256, pow2_ceil(k));
+    int ty = 256 / tx;
+    int64_t gx = ceil_div(k, tx);
+    int64_t gy = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->sm_count * 4 / gx,
+                                                        ceil_div(std::max<int64_t>(n, 1), (int64_t)ty * 4)));
+    gy = std::min<int64_t>(gy, 65535);
+    int64_t rows = std::max<int64_t>(1, ceil_div(std::max<int64_t>(n, 1), gy));
+    gy = std::max<int64_t>(1, ceil_div(n, rows));
+    DBuf<AbsMax> partial(ctx, (size_t)(gy * k));
+    KTimer kt(ctx, kname<T>("colabsmax_f32", "colabsmax_f64"), (double)n * k * sizeof(T));
+    colabsmax_kernel<T><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(S, n, k, ld, partial.p, tx, rows);
+    check_launch(ctx);
+    colabsmax_final_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(partial.p, gy, k, out3);
+    check_launch(ctx);
+}
+
+// flip[j] in {+1,-1}; S[:, j] *= flip[j] (n x k) and C[j, :] *= flip[j] (k x d)
+template <typename T>
+__global__ void apply_flip_kernel(T* S, int64_t n, int64_t k, int64_t lds, T* C, int64_t d,
+                                  const double* __restrict__ flip3 /* [k][3], sign at +2 */) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t ns = S ? n * k : 0;
+    if (idx < ns) {
+        int64_t r = idx / k, j = idx % k;
+        if (flip3[j * 3 + 2] < 0.0) S[r * lds + j] = -S[r * lds + j];
+    } else if (idx < ns + k * d) {
+        int64_t e = idx - ns;
+        int64_t j = e / d;
+        if (flip3[j * 3 + 2] < 0.0) C[e] = -C[e];
+    }
+}
+
+template <typename T>
+void launch_apply_flip(petal_ctx* ctx, T* S, int64_t n, int64_t k, int64_t lds, T* C, int64_t d,
+                       const double* flip3) {
+    int64_t total = (S ? n * k : 0) + k * d;
+    if (total == 0) return;
+    apply_flip_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, ctx->stream>>>(S, n, k, lds, C, d, flip3);
+    check_launch(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// small elementwise helpers
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, int64_t count, double scale) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = (TO)((double)in[i] * scale);
+}
+
+template <typename TI, typename TO>
+void launch_cast(petal_ctx* ctx, const TI* in, TO* out, int64_t count, double scale = 1.0) {
+    if (count == 0) return;
+    cast_kernel<TI, TO><<<(unsigned)ceil_div(count, 256), 256, 0, ctx->stream>>>(in, out, count, scale);
+    check_launch(ctx);
+}
+
+// out[c][r] = in[r][c]
+__global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols,
+                                 double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    int64_t r0 = (int64_t)blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        int64_t r = r0 + y;
+        tile[y][threadIdx.x] = (r < rows && c < cols) ? in[r * cols + c] : 0.0;
+    }
+    __syncthreads();
+    int64_t orow0 = (int64_t)blockIdx.x * 32;
+    int64_t ocol = r0 + threadIdx.x;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        int64_t orow = orow0 + y;
+        if (orow < cols && ocol < rows) out[orow * rows + ocol] = tile[threadIdx.x][y];
+    }
+}
+
+inline void launch_transpose(petal_ctx* ctx, const double* in, int64_t rows, int64_t cols, double* out) {
+    if (rows == 0 || cols == 0) return;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    transpose_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(in, rows, cols, out);
+    check_launch(ctx);
+}
+
+}  // namespace petal
