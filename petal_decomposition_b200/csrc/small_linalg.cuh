@@ -259,7 +259,10 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     if (m == 0) return 0;
     if (m > (int64_t)1 << 20 || len > (int64_t)1 << 30) invalid_input("matrix too large for the Jacobi solver");
     const int max_sweeps = 60;
-    const double tol = 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
+    // |<a_p, a_q>| <= tol * |a_p| |a_q| counts as orthogonal. The computed inner product carries
+    // ~sqrt(len) * eps of rounding noise, so the threshold sits a small factor above that - a
+    // tighter one never reports a rotation-free sweep and runs to max_sweeps.
+    const double tol = 8.0 * 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
     size_t smem = ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double);
     KTimer kt(ctx, "jacobi", 0.0);
     if (!force_global && smem <= 200 * 1024) {

@@ -209,12 +209,19 @@ def test_colmean_gram(pd, dtype, n, d):
 
 # ------------------------------------------------------------ exact PCA vs oracle
 def _check_pca(model, ref, x, tol_s, tol_c, k):
-    assert rel(model.singular_values(), ref.singular_values()) < tol_s
-    assert rel(model.explained_variance_ratio(), ref.explained_variance_ratio()) < tol_s
+    s, sr = np.asarray(model.singular_values(), np.float64), np.asarray(ref.singular_values(), np.float64)
+    big = sr > 1e-4 * sr[0]
+    # relative tolerance on every singular value that is not numerically zero; the Gram route
+    # resolves exact zeros (rank-deficient data) only to sqrt(eps) * sigma_max
+    assert rel(s[big], sr[big]) < tol_s
+    assert np.all(np.abs(s[~big] - sr[~big]) < 1e-7 * sr[0])
+    ev, evr = model.explained_variance_ratio(), ref.explained_variance_ratio()
+    assert rel(ev[big], evr[big]) < 2 * tol_s and np.all(np.abs(ev[~big] - evr[~big]) < 1e-13)
     assert abs(model._total_variance - ref.total_variance) < tol_s * ref.total_variance
     assert np.allclose(model.mean(), ref.means, rtol=tol_s, atol=tol_s)
-    cm = opca.sign_normalize_rows(model.components())
-    cr = opca.sign_normalize_rows(ref.components)
+    kk = int(np.sum(big))
+    cm = opca.sign_normalize_rows(model.components()[:kk])
+    cr = opca.sign_normalize_rows(ref.components[:kk])
     assert np.max(np.abs(cm - cr)) < tol_c
 
 
@@ -226,8 +233,9 @@ def test_pca_f64_vs_oracle(pd, n, d, k):
     m = pd.Pca.new(k)
     y = m.fit_transform(x)
     _check_pca(m, ref, x, 1e-10, 1e-7, k)
-    # u-based svd_flip makes signs comparable directly
-    assert np.allclose(m.components(), ref.components, atol=1e-7)
+    # u-based svd_flip makes signs comparable directly (for the non-null components)
+    kk = int(np.sum(ref.singular_values() > 1e-4 * ref.singular_values()[0]))
+    assert np.allclose(m.components()[:kk], ref.components[:kk], atol=1e-7)
     assert np.allclose(y, yr, atol=1e-8 * np.abs(yr).max())
     assert np.allclose(m.transform(x), ref.transform(x), atol=1e-8 * np.abs(yr).max())
     z = m.inverse_transform(y)
@@ -311,12 +319,46 @@ def test_fastica_vs_oracle(pd, dtype, n, d):
     sr = ref.fit_transform(x.astype(np.float64), w_init.astype(np.float64))
     ica = pd.FastIca.with_seed(RNG_SEED)
     s = ica.fit_transform(x)
-    assert ica.n_iter < 200 and abs(ica.n_iter - ref.n_iter) <= 1
+    # The whitening eigenvectors are defined up to sign (LAPACK backends differ among themselves),
+    # so the two runs start from sign-flipped coordinates: trajectories differ, the fixed point is
+    # the same up to the convergence tolerance (tol = 1e-4 on the rows of W).
+    assert ica.n_iter < 200 and abs(ica.n_iter - ref.n_iter) <= 4
     matched, defect = oica.match_rows(ica.components, ref.components)
-    assert defect < (1e-8 if dtype == np.float64 else 1e-4)
+    assert defect < 1e-6  # 1 - |cos| of matched unmixing rows
     assert oica.amari_index(ica.components, a) < 0.05
     assert np.allclose(ica.transform(x), s, atol=1e-10 if dtype == np.float64 else 1e-3)
     assert np.allclose(np.asarray(s).std(axis=0), np.asarray(sr).std(axis=0)[0], rtol=0.05)
+
+
+@pytest.mark.parametrize("n,d", [(5000, 3), (20000, 6), (8000, 16)])
+def test_ica_par_trajectory_vs_oracle(pd, n, d):
+    """Same whitened input, same w_init: the fixed-point trajectory must agree with the oracle
+    iteration by iteration (identical n_iter, W to 1e-9)."""
+    x, _ = synth.mixed_sources(n, d, seed=d + 1)
+    xc = (x - x.mean(axis=0)).T
+    u, s, _ = np.linalg.svd(xc, full_matrices=False)
+    x1 = ((u / s).T @ xc) * np.sqrt(n)
+    w_init = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(d, d)
+    wr, nr = oica.ica_par(x1, 1e-4, 200, w_init)
+    w, ni = pd.ica_par(np.ascontiguousarray(x1.T), 1e-4, 200, w_init)
+    assert ni == nr
+    assert np.allclose(w, wr, atol=1e-9)
+    for fun, name in [(pd.EXP, "exp"), (pd.CUBE, "cube")]:
+        w2, n2 = pd.ica_par(np.ascontiguousarray(x1.T), 1e-4, 200, w_init, fun=fun)
+        assert np.allclose(w2 @ w2.T, np.eye(d), atol=1e-10) and n2 <= 200
+
+
+def test_fastica_tight_tolerance_matches_oracle(pd):
+    """Converged to 1e-12 both runs reach the same fixed point whatever the starting signs."""
+    x, a = synth.mixed_sources(20000, 5, seed=9)
+    w_init = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(5, 5)
+    ref = oica.FastIca(tol=1e-12, max_iter=1000)
+    ref.fit(x, w_init)
+    ica = pd.FastIca(pd.Pcg.from_seed(RNG_SEED), tol=1e-12, max_iter=1000)
+    ica.fit(x)
+    matched, defect = oica.match_rows(ica.components, ref.components)
+    assert defect < 1e-12
+    assert np.allclose(matched, ref.components, atol=1e-7 * np.abs(ref.components).max())
 
 
 def test_fastica_d3_literal_reference_diverges(pd):
