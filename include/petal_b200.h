@@ -177,6 +177,13 @@ int petal_colmean_gram_f32(petal_ctx* ctx, const float* x, int64_t n, int64_t d,
 int petal_colmean_gram_f64(petal_ctx* ctx, const double* x, int64_t n, int64_t d, int centering,
                            double* mean, double* gram);
 
+/* out[d*l] (f64) = (x - mean)^T y  with x[n*d], y[n*l] (mean may be NULL): the X^T*Q / Q^T*X pass of
+ * the range finder (src/pca.rs:681,711), all-reduced over ranks. */
+int petal_xty_f32(petal_ctx* ctx, const float* x, int64_t n, int64_t d, const float* mean, const float* y,
+                  int64_t l, double* out);
+int petal_xty_f64(petal_ctx* ctx, const double* x, int64_t n, int64_t d, const double* mean, const double* y,
+                  int64_t l, double* out);
+
 #ifdef __cplusplus
 }
 #endif

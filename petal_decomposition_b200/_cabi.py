@@ -23,6 +23,7 @@ _TYPED = {
     "petal_fastica_fit": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_int, c_vp, c_vp, c_vp,
                                   C.POINTER(c_i64), C.POINTER(c_dbl), c_vp]),
     "petal_colmean_gram": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
+    "petal_xty": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
 }
 SYMBOLS = {
     "petal_ctx_create": (c_int, [c_int, C.POINTER(c_vp)]),

@@ -616,3 +616,16 @@ def colmean_gram(x, centering: bool = True, ctx: Context | None = None):
     fn = getattr(ctx.lib, f"petal_colmean_gram_{a.suffix}")
     ctx.check(fn(ctx.handle, a.ptr, n, d, int(centering), _np_ptr(mean), _np_ptr(gram)))
     return mean, gram
+
+
+def xty(x, y, mean=None, ctx: Context | None = None) -> np.ndarray:
+    """(x - mean)^T y as an f64 host matrix (the X^T*Q pass of the range finder)."""
+    a, b = _Arr(x), _Arr(y)
+    ctx = _ctx_for(ctx)
+    n, d = a.shape
+    l = b.shape[1]
+    mu = None if mean is None else np.ascontiguousarray(mean, dtype=a.dtype)
+    out = np.zeros((d, l))
+    fn = getattr(ctx.lib, f"petal_xty_{a.suffix}")
+    ctx.check(fn(ctx.handle, a.ptr, n, d, _np_ptr(mu), b.ptr, l, _np_ptr(out)))
+    return out

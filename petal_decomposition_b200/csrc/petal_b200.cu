@@ -9,10 +9,14 @@
 #include "common.cuh"
 #include "small_linalg.cuh"
 #include "stream_kernels.cuh"
+#include "tc_kernels.cuh"
 
 using namespace petal;
 
 namespace {
+
+// relative entry noise of a Gram matrix accumulated in f64 (orthogonality floor of the Jacobi solver)
+const double kGramNoise = 4.0 * 2.220446049250313e-16;
 
 std::string g_global_error;
 std::mutex g_global_mutex;
@@ -195,10 +199,32 @@ void centered_gram(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld,
 template <typename T>
 void gemm_xb(petal_ctx* ctx, const T* A, int64_t lda, int64_t n, int64_t K, const T* B, int64_t ldb,
              bool b_trans, int64_t L, const T* mu, const T* bias, T* Y, int64_t ldy, double* sumsq = nullptr) {
+    if constexpr (sizeof(T) == 4) {
+        if (ctx->f32_engine == 1 && bias == nullptr && tc::xb_supported(A, lda, n, K, L) && is_aligned16(mu)) {
+            tc::launch_tc_xb<float>(ctx, A, lda, n, K, B, ldb, b_trans, L, mu, Y, ldy, sumsq);
+            return;
+        }
+    }
     XbParams<T> p{};
     p.A = A; p.lda = lda; p.n = n; p.K = K; p.B = B; p.ldb = ldb; p.b_trans = b_trans ? 1 : 0; p.L = L;
     p.mu = mu; p.bias = bias; p.Y = Y; p.ldy = ldy; p.sumsq = sumsq;
     launch_xb<T>(ctx, p);
+}
+
+// Y = (A - mu) * B with B given in f64 (small replicated matrix): the tcgen05 engine splits B into
+// hi/lo straight from the f64 values; the SIMT engine gets a rounded copy.
+template <typename T>
+void gemm_xb_b64(petal_ctx* ctx, const T* A, int64_t lda, int64_t n, int64_t K, const double* B, int64_t ldb,
+                 int64_t L, const T* mu, T* Y, int64_t ldy) {
+    if constexpr (sizeof(T) == 4) {
+        if (ctx->f32_engine == 1 && tc::xb_supported(A, lda, n, K, L) && is_aligned16(mu)) {
+            tc::launch_tc_xb<double>(ctx, A, lda, n, K, B, ldb, false, L, mu, Y, ldy, nullptr);
+            return;
+        }
+    }
+    DBuf<T> Bt(ctx, (size_t)(K * ldb));
+    launch_cast<double, T>(ctx, B, Bt.p, K * ldb);
+    gemm_xb<T>(ctx, A, lda, n, K, Bt.p, ldb, false, L, mu, nullptr, Y, ldy);
 }
 
 // C[da x db] (f64, zeroed here) = (A - mua)^T (B - mub)
@@ -206,6 +232,13 @@ template <typename T>
 void gemm_atb(petal_ctx* ctx, const T* A, int64_t lda, int64_t da, const T* mua, const T* B, int64_t ldb,
               int64_t db, const T* mub, int64_t n, double* C) {
     PETAL_CUDA(cudaMemsetAsync(C, 0, (size_t)(da * db) * sizeof(double), ctx->stream));
+    if constexpr (sizeof(T) == 4) {
+        if (ctx->f32_engine == 1 && mub == nullptr && tc::atb_supported(A, lda, da, B, ldb, db, n) &&
+            is_aligned16(mua)) {
+            tc::launch_tc_atb(ctx, A, lda, da, mua, B, ldb, db, n, C, db);
+            return;
+        }
+    }
     AtbParams<T> p{};
     p.A = A; p.lda = lda; p.da = da; p.mua = mua; p.B = B; p.ldb = ldb; p.db = db; p.mub = mub;
     p.n = n; p.C = C; p.ldc = db; p.symmetric = 0;
@@ -225,12 +258,11 @@ double rank_cutoff() {
 // Plays the role of the reference's re-normalisation between power iterations
 // (lu::Factorized::into_pl, src/pca.rs:709-713) - same range, better conditioned.
 void orthonormalize_columns(petal_ctx* ctx, double* Z, int64_t rows, int64_t l, double cutoff) {
-    DBuf<double> G(ctx, (size_t)(l * l)), Jt(ctx, (size_t)(l * l)), sig(ctx, (size_t)l), P(ctx, (size_t)(l * l));
+    DBuf<double> G(ctx, (size_t)(l * l)), P(ctx, (size_t)(l * l));
     DBuf<double> Z1(ctx, (size_t)(rows * l));
     for (int round = 0; round < 2; ++round) {
         gemm_atb<double>(ctx, Z, l, l, nullptr, Z, l, l, nullptr, rows, G.p);
-        jacobi_rows(ctx, G.p, l, l, nullptr, Jt.p, sig.p);
-        launch_scaled_transpose(ctx, Jt.p, sig.p, l, 0, round == 0 ? cutoff : 1e-6, P.p);
+        gram_to_orthonormalizer(ctx, G.p, l, round == 0 ? cutoff : 1e-6, kGramNoise, P.p);
         gemm_xb<double>(ctx, Z, l, rows, l, P.p, l, false, l, nullptr, nullptr, Z1.p, l);
         PETAL_CUDA(cudaMemcpyAsync(Z, Z1.p, (size_t)(rows * l) * sizeof(double), cudaMemcpyDeviceToDevice,
                                    ctx->stream));
@@ -289,7 +321,7 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
     centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
     trace_kernel<<<1, 256, 0, ctx->stream>>>(G.p, d, tvd.p);  // sum of all sigma^2, src/pca.rs:224
     launch1(ctx);
-    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p);
+    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p, kGramNoise);
 
     DBuf<T> comps_tmp;
     T* comps_dev = comps.p;
@@ -351,50 +383,64 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     const double cutoff = rank_cutoff<T>();
 
     // Y = Xc * Omega (src/pca.rs:707), fused with ||Xc||_F^2 (src/pca.rs:533)
-    DBuf<T> Y(ctx, (size_t)(n * l));
+    const int64_t ly = ((l + 3) / 4) * 4;  // row pitch of Y: 16 B multiple so TMA can stream it
+    DBuf<T> Y(ctx, (size_t)(n * ly));
     DBuf<double> small(ctx, (size_t)(l * l + d * l + 1));  // [G2 | C' | tv] reduced together
     double* G2 = small.p;
     double* Cp = small.p + l * l;
     double* tvd = small.p + l * l + d * l;
     PETAL_CUDA(cudaMemsetAsync(tvd, 0, sizeof(double), ctx->stream));
-    gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, l, tvd);
+    gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
 
     // power iterations (src/pca.rs:708-715): Z = Xc^T Y, re-orthonormalise, Y = Xc Z
     DBuf<double> Zd(ctx, (size_t)(d * l));
-    DBuf<T> Zt(ctx, (size_t)(d * l));
     for (int64_t it = 0; it < n_iter; ++it) {
-        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, l, l, nullptr, n, Zd.p);
+        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, ly, l, nullptr, n, Zd.p);
         allreduce_sum(ctx, Zd.p, (size_t)(d * l));
         orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
-        launch_cast<double, T>(ctx, Zd.p, Zt.p, d * l);
-        gemm_xb<T>(ctx, X.p, d, n, d, Zt.p, l, false, l, cm.mu, nullptr, Y.p, l);
+        gemm_xb_b64<T>(ctx, X.p, d, n, d, Zd.p, l, l, cm.mu, Y.p, ly);
     }
 
     // thin QR of Y (src/pca.rs:716) done implicitly in two Gram rounds (CholeskyQR2-style, with a
     // Jacobi eigensolver instead of Cholesky so that rank-deficient Y is handled):
     //   round 1: Y1 = Y * P1 (materialised),  round 2: Q = Y1 * P2 (implicit)
-    DBuf<double> G1(ctx, (size_t)(l * l)), JtG(ctx, (size_t)(l * l)), sigG(ctx, (size_t)l), P(ctx, (size_t)(l * l));
-    DBuf<T> Pt(ctx, (size_t)(l * l));
-    DBuf<T> Y1(ctx, (size_t)(n * l));
-    gemm_atb<T>(ctx, Y.p, l, l, nullptr, Y.p, l, l, nullptr, n, G1.p);
+    DBuf<double> G1(ctx, (size_t)(l * l)), P(ctx, (size_t)(l * l));
+    DBuf<T> Y1(ctx, (size_t)(n * ly));
+    gemm_atb<T>(ctx, Y.p, ly, l, nullptr, Y.p, ly, l, nullptr, n, G1.p);
     allreduce_sum(ctx, G1.p, (size_t)(l * l));
-    jacobi_rows(ctx, G1.p, l, l, nullptr, JtG.p, sigG.p);
-    launch_scaled_transpose(ctx, JtG.p, sigG.p, l, 0, cutoff, P.p);
-    launch_cast<double, T>(ctx, P.p, Pt.p, l * l);
-    gemm_xb<T>(ctx, Y.p, l, n, l, Pt.p, l, false, l, nullptr, nullptr, Y1.p, l);
+    gram_to_orthonormalizer(ctx, G1.p, l, cutoff, kGramNoise, P.p);
+    gemm_xb_b64<T>(ctx, Y.p, ly, n, l, P.p, l, l, nullptr, Y1.p, ly);
     // B = Q^T Xc (src/pca.rs:681) = P2^T (Y1^T Xc):  C' = Xc^T Y1 (d x l) in one pass over X
-    gemm_atb<T>(ctx, Y1.p, l, l, nullptr, Y1.p, l, l, nullptr, n, G2);
-    gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, l, l, nullptr, n, Cp);
+    gemm_atb<T>(ctx, Y1.p, ly, l, nullptr, Y1.p, ly, l, nullptr, n, G2);
+    gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, ly, l, nullptr, n, Cp);
     allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
-    jacobi_rows(ctx, G2, l, l, nullptr, JtG.p, sigG.p);
-    launch_scaled_transpose(ctx, JtG.p, sigG.p, l, 0, 1e-6, P.p);  // P2 (l x l)
+    gram_to_orthonormalizer(ctx, G2, l, 1e-6, kGramNoise, P.p);  // P2 (l x l)
     DBuf<double> M1(ctx, (size_t)(d * l)), Bm(ctx, (size_t)(l * d));
     gemm_xb<double>(ctx, Cp, l, d, l, P.p, l, false, l, nullptr, nullptr, M1.p, l);
     launch_transpose(ctx, M1.p, d, l, Bm.p);  // B (l x d)
 
-    // SVD of B (src/pca.rs:682, gesdd): rows of Jt*B orthogonal
+    // SVD of B (src/pca.rs:682, gesdd).  B is l x d with l << d: first diagonalise the small Gram
+    // B B^T = W diag(s^2) W^T (single-CTA Jacobi), rotate B' = W^T B (rows now orthogonal up to
+    // eps * cond^2), then let the one-sided Jacobi on B' clean up (f64 API; it converges in a
+    // sweep or two from there).  For the f32 API the Gram route is already far below the 1e-4
+    // tolerance and B' is final.
     DBuf<double> Bout(ctx, (size_t)(l * d)), JtB(ctx, (size_t)(l * l)), sigB(ctx, (size_t)l), Vt(ctx, (size_t)(l * d));
-    jacobi_rows(ctx, Bm.p, l, d, Bout.p, JtB.p, sigB.p);
+    {
+        DBuf<double> GB(ctx, (size_t)(l * l)), W1(ctx, (size_t)(l * l)), lamB(ctx, (size_t)l), Bp(ctx, (size_t)(l * d));
+        gemm_xb<double>(ctx, Bm.p, d, l, d, Bm.p, d, true, l, nullptr, nullptr, GB.p, l);   // B B^T
+        jacobi_rows(ctx, GB.p, l, l, nullptr, W1.p, lamB.p, kGramNoise);                               // rows of W1 = eigenvectors
+        gemm_xb<double>(ctx, W1.p, l, l, l, Bm.p, d, false, d, nullptr, nullptr, Bp.p, d);  // B' = W1 B
+        if (sizeof(T) == 4) {
+            row_norm_kernel<<<(unsigned)l, 256, 0, ctx->stream>>>(Bp.p, (int)l, (int)d, sigB.p);
+            launch1(ctx);
+            PETAL_CUDA(cudaMemcpyAsync(Bout.p, Bp.p, (size_t)(l * d) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            PETAL_CUDA(cudaMemcpyAsync(JtB.p, W1.p, (size_t)(l * l) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            DBuf<double> J2(ctx, (size_t)(l * l));
+            jacobi_rows(ctx, Bp.p, l, d, Bout.p, J2.p, sigB.p);
+            gemm_xb<double>(ctx, J2.p, l, l, l, W1.p, l, false, l, nullptr, nullptr, JtB.p, l);  // Jt = J2 W1
+        }
+    }
     launch_normalize_rows(ctx, Bout.p, sigB.p, l, d, 0.0, Vt.p);
 
     DBuf<T> comps_tmp;
@@ -408,18 +454,16 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     if (k > 0) {
         // U * Sigma = Q * U_B * Sigma (src/pca.rs:683, transform_with_u) = Y1 * (P2 * U_B[:, :k] * Sigma_k)
         DBuf<double> S(ctx, (size_t)(l * k));
-        DBuf<T> St(ctx, (size_t)(l * k));
         gemm_xb<double>(ctx, P.p, l, l, l, JtB.p, l, true, k, nullptr, nullptr, S.p, k);
         scale_cols_kernel<<<(unsigned)ceil_div(l * k, 256), 256, 0, ctx->stream>>>(S.p, l, k, sigB.p);
         launch1(ctx);
-        launch_cast<double, T>(ctx, S.p, St.p, l * k);
         DBuf<T> scores_tmp;
         T* scores_dev = scores.p;
         if (!scores_dev) {
             scores_tmp.alloc(ctx, (size_t)(n * k));
             scores_dev = scores_tmp.p;
         }
-        gemm_xb<T>(ctx, Y1.p, l, n, l, St.p, k, false, k, nullptr, nullptr, scores_dev, k);
+        gemm_xb_b64<T>(ctx, Y1.p, ly, n, l, S.p, k, k, nullptr, scores_dev, k);
         flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d);  // svd_flip, src/pca.rs:684
         if (sing) launch_cast<double, T>(ctx, sigB.p, sing.p, k);
     }
@@ -554,7 +598,7 @@ void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun,
     // matrix; the same U, sigma^2 are the eigenpairs of the d x d Gram Xc^T Xc.
     DBuf<double> G(ctx, (size_t)(d * d)), Jt(ctx, (size_t)(d * d)), lam(ctx, (size_t)d);
     centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
-    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p);
+    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p, kGramNoise);
     DBuf<double> K(ctx, (size_t)(nc * d)), K1(ctx, (size_t)(nc * d));
     whitening_kernel<<<(unsigned)ceil_div(nc * d, 256), 256, 0, ctx->stream>>>(Jt.p, lam.p, nc, d, 1.0, K.p);
     launch1(ctx);
@@ -783,6 +827,23 @@ int petal_comm_init(petal_ctx* ctx, const void* id, int rank, int world_size) {
             finish_call(ctx, m.to_host || g.to_host);                                                          \
         });                                                                                                    \
     }
+
+#define PETAL_DEFINE_XTY(SUFFIX, T)                                                                            \
+    int petal_xty_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, const T* mean, const T* y, int64_t l, \
+                           double* out) {                                                                      \
+        return guarded(ctx, [&] {                                                                              \
+            if (n <= 0 || d <= 0 || l <= 0) invalid_input("empty input");                                      \
+            DevIn<T> X(ctx, x, (size_t)(n * d)), Y(ctx, y, (size_t)(n * l)), mu(ctx, mean, (size_t)d);         \
+            DevOut<double> O(ctx, out, (size_t)(d * l));                                                       \
+            if (!O) invalid_input("output buffer is null");                                                    \
+            gemm_atb<T>(ctx, X.p, d, d, mu.p, Y.p, l, l, nullptr, n, O.p);                                     \
+            allreduce_sum(ctx, O.p, (size_t)(d * l));                                                          \
+            O.commit(ctx);                                                                                     \
+            finish_call(ctx, O.to_host);                                                                       \
+        });                                                                                                    \
+    }
+PETAL_DEFINE_XTY(f32, float)
+PETAL_DEFINE_XTY(f64, double)
 
 PETAL_DEFINE_TYPED(f32, float)
 PETAL_DEFINE_TYPED(f64, double)

@@ -44,9 +44,13 @@ __device__ __forceinline__ void rr_pair(int me, int s, int i, int& p, int& q) {
 }
 
 // Computes the rotation for a row pair; returns false when already orthogonal to tolerance.
-__device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol,
+// `noise` = (relative entry noise of the input) * (largest row norm): rows of a Gram matrix carry
+// absolute noise eps * lambda_max from the start, so two small rows cannot be made orthogonal
+// beyond that floor - without the floor the sweep loop never reports convergence.
+__device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol, double noise,
                                                 double& c, double& s) {
-    if (!(fabs(gamma) > tol * sqrt(alpha) * sqrt(beta))) return false;  // also false for NaN/zero rows
+    const double na = sqrt(alpha), nb = sqrt(beta);
+    if (!(fabs(gamma) > tol * na * nb + noise * (na + nb))) return false;  // also false for NaN/zero rows
     double zeta = (beta - alpha) / (2.0 * gamma);
     double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     c = rsqrt(1.0 + t * t);
@@ -57,12 +61,19 @@ __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, doubl
 // ------------------------------------------------------------------------------------------
 // single-CTA engine
 // ------------------------------------------------------------------------------------------
-constexpr int kJacobiSmemThreads = 512;
+constexpr int kJacobiSmemThreads = 1024;
+
+__device__ __forceinline__ double group16_sum(double v, unsigned mask) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+}
 
 __global__ void __launch_bounds__(kJacobiSmemThreads)
 jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restrict__ Aout,
                    double* __restrict__ Jt, double* __restrict__ sig, int max_sweeps, double tol,
-                   int* __restrict__ info) {
+                   double noise_rel, const int* __restrict__ run_flag, int* __restrict__ info) {
+    if (run_flag != nullptr && *run_flag == 0) return;  // fast path succeeded: nothing to do
     extern __shared__ double sm[];
     double* M = sm;                       // m x len
     double* J = sm + (size_t)m * len;     // m x m
@@ -75,42 +86,57 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
     for (int i = tid; i < m * m; i += kJacobiSmemThreads) J[i] = ((i / m) == (i % m)) ? 1.0 : 0.0;
     if (tid == 0) rotated = 0;
     __syncthreads();
+    // largest row norm (for the input-noise floor)
+    for (int j = warp; j < m; j += nwarps) {
+        double a = 0.0;
+        for (int e = lane; e < len; e += 32) a += M[(size_t)j * len + e] * M[(size_t)j * len + e];
+        a = warp_sum(a);
+        if (lane == 0) nrm[j] = a;
+    }
+    __syncthreads();
+    double amax = 0.0;
+    for (int j = 0; j < m; ++j) amax = fmax(amax, nrm[j]);
+    const double noise = noise_rel * sqrt(amax);
+    __syncthreads();
 
     const int me = (m + 1) & ~1;
     int sweeps = 0;
+    // one 16-lane group per row pair: all pairs of a round-robin step run concurrently
+    const int gid = tid >> 4, gl = tid & 15, ngroups = kJacobiSmemThreads / 16;
+    const unsigned gmask = 0xFFFFu << (lane & 16);
     for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
         for (int step = 0; step < me - 1; ++step) {
-            for (int pi = warp; pi < me / 2; pi += nwarps) {
+            for (int pi = gid; pi < me / 2; pi += ngroups) {
                 int p, q;
                 rr_pair(me, step, pi, p, q);
                 if (q >= m) continue;
                 double* mp = M + (size_t)p * len;
                 double* mq = M + (size_t)q * len;
                 double al = 0.0, be = 0.0, ga = 0.0;
-                for (int e = lane; e < len; e += 32) {
+                for (int e = gl; e < len; e += 16) {
                     double x = mp[e], y = mq[e];
                     al += x * x;
                     be += y * y;
                     ga += x * y;
                 }
-                al = warp_sum(al);
-                be = warp_sum(be);
-                ga = warp_sum(ga);
+                al = group16_sum(al, gmask);
+                be = group16_sum(be, gmask);
+                ga = group16_sum(ga, gmask);
                 double c, s;
-                if (!jacobi_rotation(al, be, ga, tol, c, s)) continue;
-                for (int e = lane; e < len; e += 32) {
+                if (!jacobi_rotation(al, be, ga, tol, noise, c, s)) continue;
+                for (int e = gl; e < len; e += 16) {
                     double x = mp[e], y = mq[e];
                     mp[e] = c * x - s * y;
                     mq[e] = s * x + c * y;
                 }
                 double* jp = J + (size_t)p * m;
                 double* jq = J + (size_t)q * m;
-                for (int e = lane; e < m; e += 32) {
+                for (int e = gl; e < m; e += 16) {
                     double x = jp[e], y = jq[e];
                     jp[e] = c * x - s * y;
                     jq[e] = s * x + c * y;
                 }
-                if (lane == 0) rotated = 1;
+                if (gl == 0) rotated = 1;
             }
             __syncthreads();
         }
@@ -159,7 +185,7 @@ __global__ void set_identity_kernel(double* J, int64_t m) {
 
 __global__ void __launch_bounds__(256)
 jacobi_step_kernel(double* __restrict__ M, int m, int len, double* __restrict__ J, int me, int step,
-                   double tol, int* __restrict__ rotated) {
+                   double tol, const double* __restrict__ noise_ptr, int* __restrict__ rotated) {
     int p, q;
     rr_pair(me, step, blockIdx.x, p, q);
     if (q >= m) return;
@@ -191,7 +217,7 @@ jacobi_step_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
         ga += red[2][w];
     }
     double c, s;
-    if (!jacobi_rotation(al, be, ga, tol, c, s)) return;
+    if (!jacobi_rotation(al, be, ga, tol, *noise_ptr, c, s)) return;
     for (int e = tid; e < len; e += 256) {
         double x = mp[e], y = mq[e];
         mp[e] = c * x - s * y;
@@ -227,6 +253,13 @@ row_norm_kernel(const double* __restrict__ M, int m, int len, double* __restrict
     }
 }
 
+// noise[0] = noise_rel * max_j nrm[j]
+__global__ void noise_floor_kernel(const double* __restrict__ nrm, int m, double noise_rel, double* __restrict__ noise) {
+    double a = 0.0;
+    for (int j = 0; j < m; ++j) a = fmax(a, nrm[j]);
+    noise[0] = noise_rel * a;
+}
+
 __global__ void __launch_bounds__(256)
 sort_scatter_kernel(const double* __restrict__ M, const double* __restrict__ J,
                     const double* __restrict__ nrm, int m, int len, double* __restrict__ Aout,
@@ -254,8 +287,17 @@ sort_scatter_kernel(const double* __restrict__ M, const double* __restrict__ J,
 
 // A[m][len] (device, f64, not modified) -> Aout[m][len] (= diag(sig) N, may be null),
 // Jt[m][m] (may be null), sig[m].  Returns the number of sweeps used (-1 if unknown).
+// input_noise_rel: relative entry noise of A (0 for an exactly given matrix; ~eps for a Gram matrix
+// accumulated in f64) - sets the orthogonality floor, see jacobi_rotation.
+inline bool jacobi_fits_smem(int64_t m, int64_t len) {
+    return ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double) <= 200 * 1024;
+}
+
+// run_flag (device, optional): when given and *run_flag == 0 the factorization is skipped (used as the
+// fallback of the Cholesky fast path; only honoured by the shared-memory engine).
 inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, double* Aout, double* Jt,
-                       double* sig, bool force_global = false) {
+                       double* sig, double input_noise_rel = 0.0, bool force_global = false,
+                       const int* run_flag = nullptr) {
     if (m == 0) return 0;
     if (m > (int64_t)1 << 20 || len > (int64_t)1 << 30) invalid_input("matrix too large for the Jacobi solver");
     const int max_sweeps = 60;
@@ -264,8 +306,9 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     // tighter one never reports a rotation-free sweep and runs to max_sweeps.
     const double tol = 8.0 * 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
     size_t smem = ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double);
-    KTimer kt(ctx, "jacobi", 0.0);
-    if (!force_global && smem <= 200 * 1024) {
+    const bool use_smem = !force_global && smem <= 200 * 1024;
+    KTimer kt(ctx, use_smem ? "jacobi_smem" : "jacobi_global", 0.0);
+    if (use_smem) {
         static bool attr_set = false;
         if (!attr_set) {
             PETAL_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -273,7 +316,7 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
             attr_set = true;
         }
         jacobi_smem_kernel<<<1, kJacobiSmemThreads, smem, ctx->stream>>>(A, (int)m, (int)len, Aout, Jt, sig,
-                                                                         max_sweeps, tol, nullptr);
+                                                                         max_sweeps, tol, input_noise_rel, run_flag, nullptr);
         check_launch(ctx);
         return -1;
     }
@@ -284,13 +327,18 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     PETAL_CUDA(cudaMemcpyAsync(M.p, A, (size_t)(m * len) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     set_identity_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, ctx->stream>>>(J.p, m);
     check_launch(ctx);
+    DBuf<double> noise(ctx, 1);
+    row_norm_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, nrm.p);
+    check_launch(ctx);
+    noise_floor_kernel<<<1, 1, 0, ctx->stream>>>(nrm.p, (int)m, input_noise_rel, noise.p);
+    check_launch(ctx);
     const int me = (int)((m + 1) & ~(int64_t)1);
     int sweeps = 0;
     for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
         rotated.zero();
         for (int step = 0; step < me - 1; ++step) {
             jacobi_step_kernel<<<me / 2, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, J.p, me, step, tol,
-                                                                rotated.p);
+                                                                noise.p, rotated.p);
             check_launch(ctx);
         }
         int h = 0;
@@ -332,7 +380,9 @@ inline void launch_normalize_rows(petal_ctx* ctx, const double* Aout, const doub
 //                                    mode 2: f = 1
 // f = 0 when s <= cutoff * s[0]  (rank-deficient directions are dropped, not amplified)
 __global__ void scaled_transpose_kernel(const double* __restrict__ Jt, const double* __restrict__ sig,
-                                        int64_t m, int mode, double cutoff, double* __restrict__ P) {
+                                        int64_t m, int mode, double cutoff, double* __restrict__ P,
+                                        const int* __restrict__ run_flag) {
+    if (run_flag != nullptr && *run_flag == 0) return;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= m * m) return;
     int64_t a = idx / m, j = idx % m;
@@ -344,10 +394,112 @@ __global__ void scaled_transpose_kernel(const double* __restrict__ Jt, const dou
 }
 
 inline void launch_scaled_transpose(petal_ctx* ctx, const double* Jt, const double* sig, int64_t m, int mode,
-                                    double cutoff, double* P) {
+                                    double cutoff, double* P, const int* run_flag = nullptr) {
     if (m == 0) return;
-    scaled_transpose_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, ctx->stream>>>(Jt, sig, m, mode, cutoff, P);
+    scaled_transpose_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, ctx->stream>>>(Jt, sig, m, mode, cutoff, P,
+                                                                                     run_flag);
     check_launch(ctx);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Cholesky fast path: G (m x m, SPD) = R^T R, P = R^-1 (upper triangular), so that Z P has orthonormal
+// columns when G = Z^T Z.  Single CTA, everything in shared memory.  Sets *fail = 1 (and leaves P
+// untouched) when a pivot drops below cutoff * max diag - the caller then falls back to the Jacobi
+// eigensolver, which handles rank-deficient G.
+// ------------------------------------------------------------------------------------------
+constexpr int kCholMax = 104;
+
+__global__ void __launch_bounds__(256)
+chol_inverse_kernel(const double* __restrict__ G, int m, double cutoff, double* __restrict__ P,
+                    int* __restrict__ fail) {
+    extern __shared__ double sm[];
+    const int ld = m + 1;
+    double* A = sm;               // m x ld : R in the upper triangle
+    double* X = sm + (size_t)m * ld;  // m x ld : R^-1
+    __shared__ double maxdiag;
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < m * m; i += 256) {
+        A[(i / m) * ld + (i % m)] = G[i];
+        X[(i / m) * ld + (i % m)] = 0.0;
+    }
+    if (tid == 0) {
+        double md = 0.0;
+        for (int i = 0; i < m; ++i) md = fmax(md, G[(size_t)i * m + i]);
+        maxdiag = md;
+        bad = !(md > 0.0) || !isfinite(md);
+    }
+    __syncthreads();
+    for (int j = 0; j < m && !bad; ++j) {
+        const double d = A[j * ld + j];
+        if (!(d > cutoff * maxdiag)) {
+            __syncthreads();
+            if (tid == 0) bad = 1;
+            __syncthreads();
+            break;
+        }
+        const double r = sqrt(d);
+        __syncthreads();
+        for (int c = j + tid; c < m; c += 256) A[j * ld + c] = (c == j) ? r : A[j * ld + c] / r;
+        __syncthreads();
+        // trailing update: A[i][c] -= R[j][i] * R[j][c] for j < i <= c
+        const int t = m - j - 1;
+        for (int e = tid; e < t * t; e += 256) {
+            const int i = j + 1 + e / t, c = j + 1 + e % t;
+            if (c >= i) A[i * ld + c] -= A[j * ld + i] * A[j * ld + c];
+        }
+        __syncthreads();
+    }
+    if (bad) {
+        if (tid == 0) *fail = 1;
+        return;
+    }
+    // back substitution, one column of R^-1 per thread
+    for (int c = tid; c < m; c += 256) {
+        X[c * ld + c] = 1.0 / A[c * ld + c];
+        for (int i = c - 1; i >= 0; --i) {
+            double acc = 0.0;
+            for (int k = i + 1; k <= c; ++k) acc += A[i * ld + k] * X[k * ld + c];
+            X[i * ld + c] = -acc / A[i * ld + i];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < m * m; i += 256) P[i] = X[(i / m) * ld + (i % m)];
+}
+
+inline bool chol_supported(int64_t m) { return m >= 1 && m <= kCholMax; }
+
+inline void launch_chol_inverse(petal_ctx* ctx, const double* G, int64_t m, double cutoff, double* P, int* fail) {
+    static bool attr_set = false;
+    size_t smem = 2 * (size_t)m * (m + 1) * sizeof(double);
+    if (!attr_set) {
+        PETAL_CUDA(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    KTimer kt(ctx, "cholesky", 0.0);
+    chol_inverse_kernel<<<1, 256, smem, ctx->stream>>>(G, (int)m, cutoff, P, fail);
+    check_launch(ctx);
+}
+
+// P (m x m) with (Z P)^T (Z P) = I on the numerical range of Z, given G = Z^T Z:
+// Cholesky when G is safely positive definite, Jacobi eigensolver (W Lambda^-1/2, null directions
+// dropped) otherwise - decided on the device, no host round trip.
+inline void gram_to_orthonormalizer(petal_ctx* ctx, const double* G, int64_t m, double cutoff, double noise_rel,
+                                    double* P) {
+    DBuf<double> Jt(ctx, (size_t)(m * m)), sig(ctx, (size_t)m);
+    if (chol_supported(m) && jacobi_fits_smem(m, m)) {
+        DBuf<int> fail(ctx, 1);
+        fail.zero();
+        // a pivot below sqrt(cutoff)-ish of the largest diagonal means the columns are numerically
+        // dependent at the level where one Cholesky round can no longer fix it
+        launch_chol_inverse(ctx, G, m, std::max(cutoff, 1e-10), P, fail.p);
+        jacobi_rows(ctx, G, m, m, nullptr, Jt.p, sig.p, noise_rel, false, fail.p);
+        launch_scaled_transpose(ctx, Jt.p, sig.p, m, 0, cutoff, P, fail.p);
+    } else {
+        jacobi_rows(ctx, G, m, m, nullptr, Jt.p, sig.p, noise_rel);
+        launch_scaled_transpose(ctx, Jt.p, sig.p, m, 0, cutoff, P);
+    }
 }
 
 }  // namespace petal

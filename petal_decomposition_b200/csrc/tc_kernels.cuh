@@ -1,0 +1,695 @@
+// tcgen05 / TMEM / TMA engine for the f32 streaming contractions (sm_100a only).
+//
+//   tc_xb  : Y[n x L]  = (X - mu) * B            X*Omega, X*P, transform    (src/pca.rs:707,714,745)
+//   tc_atb : Z[da x L] += (X - mu)^T * Y          X^T*Q, Q^T*X               (src/pca.rs:681,711)
+//
+// fp32 accuracy is kept with the 3xTF32 split: every operand v is used as hi = tf32(v) (the tensor
+// core truncates the low 13 mantissa bits itself) and lo = v - hi (exact in fp32), and each product is
+// accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator.
+//
+// Data flow per CTA (persistent, 1 CTA / SM, 384 threads):
+//   warp 8   TMA producer : X tile (+ B / Y tile) -> shared memory ring (mbarrier complete_tx)
+//   warps 0-7 transform   : shared X tile -> registers: subtract mu, split hi/lo -> tcgen05.st into a
+//                           TMEM operand ring (A operand of the MMA lives in TMEM: lane = output row);
+//                           for tc_atb this is also where the X tile is transposed (lane = feature)
+//                           and where the Y tile is transposed + split into K-major Y_hi / Y_lo tiles
+//   warp 9   MMA issuer   : tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory descriptors),
+//                           3 MMAs per K-step, accumulators (2 x 128 x N fp32) stay in TMEM
+//   warps 0-7 epilogue    : tcgen05.ld accumulators -> global (tc_xb: rows of Y; tc_atb: f64 atomics)
+// The centred copy of X never exists; mu is subtracted in the transform stage.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace petal {
+namespace tc {
+
+constexpr int kThreads = 384;
+constexpr int kTransformWarps = 8;
+constexpr int kMT = 2;            // M tiles (128 TMEM lanes each) per CTA
+constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
+constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
+constexpr int kTmemCols = 512;
+constexpr int kAStageCols = kMT * 64;  // per TMEM operand stage: MT x (32 hi + 32 lo) columns
+constexpr int kAccBase = 2 * kAStageCols;  // accumulators start after the two operand stages (256)
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (it == 64) t0 = clock64();
+        if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {
+            printf("petal tc kernel: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]),
+        "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]),
+        "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (sm_100 UMMA): SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor kind::tf32, fp32 accumulate, M = 128, N = n, A K-major (TMEM), B major as given
+__host__ __device__ inline uint32_t make_idesc_tf32(int n, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(b_mn_major ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(128 >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------------
+struct TcParams {
+    CUtensorMap map_x;    // tc_xb : X as {K inner, rows}, box {32, 256}, SWIZZLE_128B
+                          // tc_atb: X as {features inner, rows}, box {256, 32}, no swizzle
+    CUtensorMap map_bhi;  // tc_xb : B^T hi as {K inner, n_pad}, box {32, n_pad}, SWIZZLE_128B
+                          // tc_atb: Y as {cols inner, rows}, box {n_pad, 32}, no swizzle
+    CUtensorMap map_blo;  // tc_xb : B^T lo (same shape as hi); unused by tc_atb
+    const float* mu_pad;  // tc_xb: [K rounded up to 32] zero padded; tc_atb: [features rounded up to 256]; never null
+    int64_t n;            // rows
+    int64_t K;            // tc_xb: reduction length (features); tc_atb: da (features)
+    int n_pad;            // MMA N (multiple of 16, <= 128)
+    int L;                // valid output columns
+    int stages;
+    // tc_xb outputs
+    float* Y;
+    int64_t ldy;
+    int y_vec;            // Y rows may be written with 16 B stores
+    double* sumsq;        // nullable
+    // tc_atb outputs / decomposition
+    double* Z;            // [da x ldz] f64, atomically accumulated
+    int64_t ldz;
+    int64_t chunk_rows;   // rows per TMEM accumulation (multiple of 32)
+    int64_t slice_rows;   // rows per CTA slice (multiple of 32)
+    int fgroups;          // feature groups of 256
+    int dbg;
+};
+
+struct SmemLayout {
+    uint32_t x, bhi, blo, mu, ylo, bars, tmem_slot, total;
+    uint32_t stage_x, stage_b, stage_mu, ylo_bytes;
+};
+
+// One carve-up shared by host (size) and device (offsets). Offsets are relative to a 1024 B aligned base.
+__host__ __device__ inline SmemLayout make_layout(bool atb, int n_pad, int stages) {
+    SmemLayout l;
+    l.stage_x = kXStageBytes;
+    l.stage_b = (uint32_t)n_pad * 128u;   // tc_xb: B^T tile [n_pad][32]; tc_atb: raw Y tile [32][n_pad]
+    l.stage_mu = 128;
+    l.ylo_bytes = atb ? 2u * (uint32_t)n_pad * 128u : 0u;  // tc_atb: K-major Y_hi | Y_lo tiles [n_pad][32]
+    uint32_t off = 0;
+    l.x = off;
+    off += (uint32_t)stages * l.stage_x;
+    l.bhi = off;
+    off += (uint32_t)stages * l.stage_b;
+    l.blo = off;
+    off += atb ? 0u : (uint32_t)stages * l.stage_b;
+    l.ylo = off;
+    off += 2u * l.ylo_bytes;
+    l.mu = off;
+    off += atb ? 0u : (uint32_t)stages * l.stage_mu;
+    l.bars = off;
+    off += 64 * 8;
+    l.tmem_slot = off;
+    off += 16;
+    l.total = off + 1024;  // slack for the 1024 B alignment of the base
+    return l;
+}
+
+inline int pick_stages(bool atb, int n_pad) {
+    for (int s = 6; s >= 2; --s)
+        if (make_layout(atb, n_pad, s).total <= 220 * 1024) return s;
+    return 0;
+}
+
+// barrier indices inside the `bars` block
+__device__ __forceinline__ uint32_t bar_full(uint32_t base, int s) { return base + 8u * (uint32_t)s; }
+__device__ __forceinline__ uint32_t bar_empty_x(uint32_t base, int s) { return base + 8u * (8 + (uint32_t)s); }
+__device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (16 + (uint32_t)s); }
+__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (24 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (26 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 28; }
+__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 29; }
+
+// ------------------------------------------------------------------------------------------
+// the kernel (ATB = false: tc_xb, ATB = true: tc_atb; NP = compile-time n_pad for tc_atb)
+//
+// Work is cut into "groups": one TMEM accumulation each.
+//   tc_xb : group = super-tile of 256 rows, K loop over ceil(K / 32) feature blocks; the epilogue
+//           stores the 256 x n_pad tile of Y.  Groups are dealt round-robin to the persistent CTAs.
+//   tc_atb: the CTA owns one feature group (256 features) and one contiguous slice of rows; a group
+//           is a chunk of <= 1024 rows of that slice (K loop over its 32-row blocks).  The tensor
+//           core adds into its fp32 accumulator with truncation, which biases long chains, so the
+//           chain is cut every chunk: the epilogue adds the chunk result into fp32 registers
+//           (round-to-nearest) and only the CTA's final sums go to global memory (f64 atomics).
+// ------------------------------------------------------------------------------------------
+struct Group {
+    int64_t row0;
+    int64_t kblocks;
+    int f0;
+};
+
+template <bool ATB>
+__device__ __forceinline__ bool get_group(const TcParams& p, int64_t g, Group& out) {
+    if (ATB) {
+        const int fg = (int)(blockIdx.x % (unsigned)p.fgroups);
+        const int64_t sl = blockIdx.x / (unsigned)p.fgroups;
+        const int64_t s0 = sl * p.slice_rows;
+        const int64_t s1 = min(p.n, s0 + p.slice_rows);
+        const int64_t r0 = s0 + g * p.chunk_rows;
+        if (r0 >= s1) return false;
+        out.row0 = r0;
+        out.kblocks = (min(p.chunk_rows, s1 - r0) + kKB - 1) / kKB;
+        out.f0 = fg * 256;
+        return true;
+    } else {
+        const int64_t item = (int64_t)blockIdx.x + g * (int64_t)gridDim.x;
+        if (item * 256 >= p.n) return false;
+        out.row0 = item * 256;
+        out.kblocks = (p.K + kKB - 1) / kKB;
+        out.f0 = 0;
+        return true;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+template <bool ATB, int NP>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int n_pad = ATB ? NP : p.n_pad;
+    const SmemLayout L = make_layout(ATB, n_pad, p.stages);
+    const uint32_t bars = base + L.bars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full(bars, s), 1);
+            mbar_init(bar_empty_x(bars, s), kTransformWarps);
+            mbar_init(bar_empty_b(bars, s), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(bar_a_ready(bars, t), kTransformWarps);
+            mbar_init(bar_a_free(bars, t), 1);
+        }
+        mbar_init(bar_acc_full(bars), 1);
+        mbar_init(bar_acc_empty(bars), kTransformWarps);
+        fence_barrier_init();
+    }
+    if (warp == 10) tmem_alloc(base + L.tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L.tmem_slot);
+    const uint32_t stage_tx = ATB ? (L.stage_x + L.stage_b) : (L.stage_x + 2u * L.stage_b + L.stage_mu);
+
+    if (warp >= kTransformWarps) {
+        if (ATB) reg_dealloc<56>();
+        if (warp == 8) {
+            // ================================ TMA producer ================================
+            if (lane == 0) {
+                uint32_t it = 0;
+                Group g;
+                for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
+                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                        const int s = (int)(it % (uint32_t)S);
+                        const uint32_t ph = (it / (uint32_t)S) & 1u;
+                        mbar_wait(bar_empty_x(bars, s), ph ^ 1u);
+                        if (!ATB) mbar_wait(bar_empty_b(bars, s), ph ^ 1u);
+                        const uint32_t full = bar_full(bars, s);
+                        mbar_expect_tx(full, stage_tx);
+                        if (ATB) {
+                            const int r = (int)(g.row0 + kb * kKB);
+                            tma_load_2d(base + L.x + (uint32_t)s * L.stage_x, &p.map_x, g.f0, r, full);
+                            tma_load_2d(base + L.bhi + (uint32_t)s * L.stage_b, &p.map_bhi, 0, r, full);
+                        } else {
+                            const int k0 = (int)(kb * kKB);
+                            tma_load_2d(base + L.x + (uint32_t)s * L.stage_x, &p.map_x, k0, (int)g.row0, full);
+                            tma_load_2d(base + L.bhi + (uint32_t)s * L.stage_b, &p.map_bhi, k0, 0, full);
+                            tma_load_2d(base + L.blo + (uint32_t)s * L.stage_b, &p.map_blo, k0, 0, full);
+                            bulk_load_1d(base + L.mu + (uint32_t)s * L.stage_mu, p.mu_pad + k0, 128, full);
+                        }
+                    }
+                }
+            }
+        } else if (warp == 9) {
+            // ================================ MMA issuer ================================
+            if (lane == 0) {
+                const uint32_t idesc = make_idesc_tf32(n_pad, 0);
+                uint32_t it = 0;
+                Group g;
+                for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
+                    mbar_wait(bar_acc_empty(bars), ((uint32_t)gi & 1u) ^ 1u);
+                    tc_fence_after();
+                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                        const int s = (int)(it % (uint32_t)S);
+                        const uint32_t ph = (it / (uint32_t)S) & 1u;
+                        const int ta = (int)(it & 1u);
+                        const uint32_t pa = (it >> 1) & 1u;
+                        // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are produced
+                        // by the transform warps together with the TMEM operand (a_ready covers both)
+                        if (!ATB) mbar_wait(bar_full(bars, s), ph);
+                        mbar_wait(bar_a_ready(bars, ta), pa);
+                        tc_fence_after();
+                        // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
+                        const uint32_t bhi_addr = ATB ? (base + L.ylo + (uint32_t)ta * L.ylo_bytes)
+                                                      : (base + L.bhi + (uint32_t)s * L.stage_b);
+                        const uint32_t blo_addr = ATB ? (bhi_addr + (uint32_t)n_pad * 128u)
+                                                      : (base + L.blo + (uint32_t)s * L.stage_b);
+#pragma unroll
+                        for (int mt = 0; mt < kMT; ++mt) {
+                            const uint32_t acc = tmem_base + (uint32_t)(kAccBase + mt * n_pad);
+                            const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kAStageCols + mt * 64);
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                // 32 B per K step inside the 128 B swizzle row
+                                const uint64_t dhi = make_desc_sw128(bhi_addr + (uint32_t)ks * 32u, 16u, 1024u);
+                                const uint64_t dlo = make_desc_sw128(blo_addr + (uint32_t)ks * 32u, 16u, 1024u);
+                                const uint32_t a_hi = a_hi0 + (uint32_t)ks * 8u;
+                                const uint32_t a_lo = a_hi + 32u;
+                                mma_tf32_ts(acc, a_lo, dhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                                mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
+                                mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
+                            }
+                        }
+                        tc_commit(bar_a_free(bars, ta));
+                        if (!ATB) tc_commit(bar_empty_b(bars, s));
+                    }
+                    tc_commit(bar_acc_full(bars));
+                }
+            }
+        }
+    } else {
+        // ================================ transform + epilogue ================================
+        if (ATB) reg_alloc<208>();
+        const int mt = warp >> 2;                 // M tile
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int lrow = q * 32 + lane;           // lane (= row / feature) inside the M tile
+        const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+        uint32_t it = 0;
+        double ss = 0.0;
+        float racc[ATB ? NP : 1];
+#pragma unroll
+        for (int j = 0; j < (ATB ? NP : 1); ++j) racc[j] = 0.f;
+        Group g;
+        g.f0 = 0;
+        for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
+            float mu_f = 0.f;
+            if (ATB) mu_f = p.mu_pad[g.f0 + mt * 128 + lrow];
+            const bool row_valid = ATB ? true : (g.row0 + mt * 128 + lrow < p.n);
+            float ssf = 0.f;
+            for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                const int s = (int)(it % (uint32_t)S);
+                const uint32_t ph = (it / (uint32_t)S) & 1u;
+                const int ta = (int)(it & 1u);
+                const uint32_t pa = (it >> 1) & 1u;
+                mbar_wait(bar_full(bars, s), ph);
+                uint32_t v[32];
+                const uint8_t* xs = base_ptr + L.x + (uint32_t)s * L.stage_x;
+                if (ATB) {
+                    // tile [32 rows][256 features] row-major: this thread owns one feature (transpose)
+                    const float* xf = reinterpret_cast<const float*>(xs) + mt * 128 + lrow;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(xf[k * 256] - mu_f);
+                } else {
+                    // tile [256 rows][32 floats], 128 B rows, SWIZZLE_128B: this thread owns one row
+                    const int r = mt * 128 + lrow;
+                    const uint8_t* xr = xs + r * 128;
+                    const float4* mus = reinterpret_cast<const float4*>(base_ptr + L.mu + (uint32_t)s * L.stage_mu);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float4 x4 = *reinterpret_cast<const float4*>(xr + ((c ^ (r & 7)) << 4));
+                        float4 m = mus[c];
+                        float e[4] = {x4.x - m.x, x4.y - m.y, x4.z - m.z, x4.w - m.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            v[c * 4 + j] = __float_as_uint(e[j]);
+                            ssf += e[j] * e[j];
+                        }
+                    }
+                    __syncwarp();  // smem X stage consumed (values are in registers)
+                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
+                }
+                // TMEM operand stage `ta` must have been drained by the MMAs of two K blocks ago
+                mbar_wait(bar_a_free(bars, ta), pa ^ 1u);
+                tc_fence_after();
+                const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kAStageCols + mt * 64);
+                tmem_st32(a_addr, v);  // hi: the tensor core ignores the low 13 mantissa bits
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float f = __uint_as_float(v[k]);
+                    v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
+                }
+                tmem_st32(a_addr + 32u, v);  // lo = v - tf32(v), exact
+                if (ATB) {
+                    // B operand of this K block: raw Y tile [32 rows][n_pad] (row-major) -> transposed
+                    // K-major tiles Y_hi / Y_lo [n_pad][32 rows] with the 128 B swizzle the MMA expects.
+                    const float* yr = reinterpret_cast<const float*>(base_ptr + L.bhi + (uint32_t)s * L.stage_b);
+                    uint8_t* bh = base_ptr + L.ylo + (uint32_t)ta * L.ylo_bytes;
+                    uint8_t* bl = bh + n_pad * 128;
+                    const int nwork = n_pad * 8;  // one 16 B chunk (4 K values of one column) each
+                    for (int i = threadIdx.x; i < nwork; i += kTransformWarps * 32) {
+                        const int nn = i % n_pad, cc = i / n_pad;
+                        float4 h, l4;
+                        h.x = yr[(cc * 4 + 0) * n_pad + nn];
+                        h.y = yr[(cc * 4 + 1) * n_pad + nn];
+                        h.z = yr[(cc * 4 + 2) * n_pad + nn];
+                        h.w = yr[(cc * 4 + 3) * n_pad + nn];
+                        l4.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u);
+                        l4.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u);
+                        l4.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u);
+                        l4.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u);
+                        const int off = nn * 128 + ((cc ^ (nn & 7)) << 4);
+                        *reinterpret_cast<float4*>(bh + off) = h;
+                        *reinterpret_cast<float4*>(bl + off) = l4;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));  // X and raw Y stage consumed
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_ready(bars, ta));
+            }
+            if (!ATB && row_valid) ss += (double)ssf;
+
+            // ---------------- epilogue for this group ----------------
+            mbar_wait(bar_acc_full(bars), (uint32_t)gi & 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad);
+            if (ATB) {
+#pragma unroll
+                for (int c0 = 0; c0 < NP; c0 += 16) {
+                    uint32_t w[16];
+                    tmem_ld16(acc + (uint32_t)c0, w);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[c0 + j] += __uint_as_float(w[j]);
+                }
+            } else {
+                const int64_t r = g.row0 + mt * 128 + lrow;
+                for (int c0 = 0; c0 < n_pad; c0 += 16) {
+                    uint32_t w[16];
+                    tmem_ld16(acc + (uint32_t)c0, w);
+                    tmem_ld_wait();
+                    if (r < p.n) {
+                        float* yr = p.Y + r * p.ldy + c0;
+                        if (p.y_vec && c0 + 16 <= p.ldy) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(yr + j) =
+                                    make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]),
+                                                __uint_as_float(w[j + 2]), __uint_as_float(w[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < p.ldy) yr[j] = __uint_as_float(w[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(bars));
+        }
+        if (ATB) {
+            // the CTA's partial (256 features x L) -> global f64 accumulator
+            const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
+            if (f < p.K) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j)
+                    if (j < p.L) atomicAdd(&p.Z[f * p.ldz + j], (double)racc[j]);
+            }
+        } else if (p.sumsq) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) atomicAdd(p.sumsq, ss);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 10) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// operand preparation (tiny kernels)
+// ------------------------------------------------------------------------------------------
+// Bt_hi / Bt_lo [n_pad][Kp] from B (K x L row-major with ldb, or L x K if b_trans); TS = float or double
+template <typename TS>
+__global__ void prep_b_kernel(const TS* __restrict__ B, int64_t ldb, int b_trans, int64_t K, int64_t Kp, int L,
+                              int n_pad, float* __restrict__ hi, float* __restrict__ lo) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_pad * Kp) return;
+    int64_t c = idx / Kp, k = idx % Kp;
+    double b = 0.0;
+    if (c < L && k < K) b = (double)(b_trans ? B[c * ldb + k] : B[k * ldb + c]);
+    float bf = (float)b;
+    float h = __uint_as_float(__float_as_uint(bf) & 0xFFFFE000u);
+    hi[idx] = h;
+    lo[idx] = (float)(b - (double)h);
+}
+
+__global__ void prep_mu_kernel(const float* __restrict__ mu, int64_t K, int64_t Kp, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Kp) out[i] = (mu != nullptr && i < K) ? mu[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PETAL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) linalg_error("cuTensorMapEncodeTiled is unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D fp32 tensor map: dims {inner, outer}, row pitch in elements
+inline CUtensorMap make_map_2d(const float* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner,
+                               uint32_t box_outer, bool swizzle128) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_elems * sizeof(float)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) linalg_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+
+inline int round_up(int64_t v, int m) { return (int)(((v + m - 1) / m) * m); }
+
+inline bool xb_supported(const void* A, int64_t lda, int64_t n, int64_t K, int64_t L) {
+    return n >= 512 && K >= 32 && L >= 1 && L <= 128 && (lda % 4 == 0) && is_aligned16(A) && n < ((int64_t)1 << 31) &&
+           K < ((int64_t)1 << 31);
+}
+
+template <bool ATB, int NP>
+inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t smem) {
+    static size_t cur = 0;
+    if (smem > cur) {
+        PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    tc_gemm_kernel<ATB, NP><<<grid, kThreads, smem, ctx->stream>>>(p);
+    check_launch(ctx);
+}
+
+// Y[n x ldy] = (A - mu) * B.  B: TS in {float, double}, K x L row-major (ldb) or L x K when b_trans.
+// Columns [L, min(ldy, n_pad)) of Y are written as zeros (padding for later TMA reads).
+template <typename TS>
+void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_t K, const TS* B, int64_t ldb,
+                  bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq) {
+    const int n_pad = round_up(L, 16);
+    const int stages = pick_stages(false, n_pad);
+    if (stages < 2) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
+    const int64_t Kp = round_up(K, 32);
+    DBuf<float> bhi(ctx, (size_t)(n_pad * Kp)), blo(ctx, (size_t)(n_pad * Kp)), mup(ctx, (size_t)Kp);
+    prep_b_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * Kp, 256), 256, 0, ctx->stream>>>(B, ldb, b_trans ? 1 : 0, K, Kp,
+                                                                                            (int)L, n_pad, bhi.p, blo.p);
+    check_launch(ctx);
+    prep_mu_kernel<<<(unsigned)ceil_div(Kp, 256), 256, 0, ctx->stream>>>(mu, K, Kp, mup.p);
+    check_launch(ctx);
+    TcParams p;
+    std::memset(&p, 0, sizeof p);
+    p.map_x = make_map_2d(A, (uint64_t)K, (uint64_t)n, (uint64_t)lda, 32, 256, true);
+    p.map_bhi = make_map_2d(bhi.p, (uint64_t)Kp, (uint64_t)n_pad, (uint64_t)Kp, 32, (uint32_t)n_pad, true);
+    p.map_blo = make_map_2d(blo.p, (uint64_t)Kp, (uint64_t)n_pad, (uint64_t)Kp, 32, (uint32_t)n_pad, true);
+    p.mu_pad = mup.p;
+    p.n = n;
+    p.K = K;
+    p.n_pad = n_pad;
+    p.L = (int)L;
+    p.stages = stages;
+    p.Y = Y;
+    p.ldy = ldy;
+    p.y_vec = (is_aligned16(Y) && (ldy % 4 == 0)) ? 1 : 0;
+    p.sumsq = sumsq;
+    const SmemLayout lay = make_layout(false, n_pad, stages);
+    const int64_t items = ceil_div(n, 256);
+    const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
+    KTimer kt(ctx, "tc_xb_f32", (double)n * (K + L) * sizeof(float));
+    launch_kernel<false, 0>(ctx, p, grid, lay.total);
+}
+
+inline bool atb_supported(const void* A, int64_t lda, int64_t da, const void* B, int64_t ldb, int64_t db, int64_t n) {
+    return n >= 1024 && da >= 32 && db >= 1 && db <= 128 && (lda % 4 == 0) && (ldb % 4 == 0) && is_aligned16(A) &&
+           is_aligned16(B) && n < ((int64_t)1 << 31) && da < ((int64_t)1 << 31);
+}
+
+// Z[da x ldz] (f64, accumulated; caller zeroes) += (A - mua)^T * B, B is n x db (ldb), not centred.
+inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t da, const float* mua, const float* B,
+                          int64_t ldb, int64_t db, int64_t n, double* Z, int64_t ldz) {
+    const int n_pad = round_up(db, 16);
+    const int stages = pick_stages(true, n_pad);
+    if (stages < 2) linalg_error("tc_atb: no pipeline configuration fits in shared memory");
+    const int fgroups = (int)ceil_div(da, 256);
+    const int64_t Fp = (int64_t)fgroups * 256;
+    DBuf<float> mup(ctx, (size_t)Fp);
+    prep_mu_kernel<<<(unsigned)ceil_div(Fp, 256), 256, 0, ctx->stream>>>(mua, da, Fp, mup.p);
+    check_launch(ctx);
+    TcParams p;
+    std::memset(&p, 0, sizeof p);
+    p.map_x = make_map_2d(A, (uint64_t)da, (uint64_t)n, (uint64_t)lda, 256, 32, false);
+    p.map_bhi = make_map_2d(B, (uint64_t)db, (uint64_t)n, (uint64_t)ldb, (uint32_t)n_pad, 32, false);
+    p.map_blo = p.map_bhi;
+    p.mu_pad = mup.p;
+    p.n = n;
+    p.K = da;
+    p.n_pad = n_pad;
+    p.L = (int)db;
+    p.stages = stages;
+    p.Z = Z;
+    p.ldz = ldz;
+    // One CTA = one feature group x one contiguous slice of rows; the TMEM accumulation chain is cut
+    // every 1024 rows (see the kernel comment).
+    const int64_t max_slices = std::max<int64_t>(1, ctx->sm_count / fgroups);
+    const int64_t slices = std::max<int64_t>(1, std::min<int64_t>(max_slices, ceil_div(n, 1024)));
+    p.chunk_rows = 1024;
+    p.slice_rows = ceil_div(ceil_div(n, slices), 32) * 32;
+    p.fgroups = fgroups;
+    p.dbg = 0;
+    const SmemLayout lay = make_layout(true, n_pad, stages);
+    const int grid = (int)(ceil_div(n, p.slice_rows) * fgroups);
+    KTimer kt(ctx, "tc_atb_f32", (double)n * (da + db) * sizeof(float));
+    switch (n_pad) {
+        case 16: launch_kernel<true, 16>(ctx, p, grid, lay.total); break;
+        case 32: launch_kernel<true, 32>(ctx, p, grid, lay.total); break;
+        case 48: launch_kernel<true, 48>(ctx, p, grid, lay.total); break;
+        case 64: launch_kernel<true, 64>(ctx, p, grid, lay.total); break;
+        case 80: launch_kernel<true, 80>(ctx, p, grid, lay.total); break;
+        case 96: launch_kernel<true, 96>(ctx, p, grid, lay.total); break;
+        case 112: launch_kernel<true, 112>(ctx, p, grid, lay.total); break;
+        default: launch_kernel<true, 128>(ctx, p, grid, lay.total); break;
+    }
+}
+
+}  // namespace tc
+}  // namespace petal

@@ -407,3 +407,47 @@ def test_launch_counter(pd):
     before = ctx.launch_count()
     pd.Pca.new(1).fit(X3)
     assert ctx.launch_count() > before
+
+
+# ------------------------------------------------------------ tcgen05 engine vs SIMT engine vs numpy
+@pytest.mark.parametrize("n,d,k", [(5000, 96, 7), (777, 100, 16), (4096, 1024, 74), (3001, 36, 1),
+                                   (2048, 260, 128), (1500, 64, 33)])
+def test_tc_xb_engines(pd, n, d, k):
+    """transform = (x - mean) C^T through the tcgen05 3xTF32 kernel and through the FFMA kernel."""
+    rng = np.random.default_rng(n + d + k)
+    x = (rng.standard_normal((n, d)) * 3 + rng.uniform(-2, 2, d)).astype(np.float32)
+    comps = rng.standard_normal((k, d)).astype(np.float32)
+    mean = x.mean(axis=0).astype(np.float32)
+    ref = (x.astype(np.float64) - mean.astype(np.float64)) @ comps.astype(np.float64).T
+    m = pd.Pca.new(k)
+    m._components, m._means = comps, mean
+    ctx = pd.default_context()
+    outs = {}
+    for eng in (0, 1):
+        ctx.set_f32_engine(eng)
+        outs[eng] = np.asarray(m.transform(x), np.float64)
+    ctx.set_f32_engine(1)
+    scale = np.abs(ref).max()
+    assert np.max(np.abs(outs[0] - ref)) < 2e-6 * scale * np.sqrt(d)
+    assert np.max(np.abs(outs[1] - ref)) < 2e-6 * scale * np.sqrt(d)
+
+
+@pytest.mark.parametrize("n,d,l", [(5000, 96, 7), (1030, 100, 16), (20000, 1024, 74), (3001, 36, 1),
+                                   (2048, 260, 128), (9000, 512, 42)])
+def test_tc_atb_engines(pd, n, d, l):
+    rng = np.random.default_rng(n + d + l)
+    x = (rng.standard_normal((n, d)) * 2 + rng.uniform(-1, 1, d)).astype(np.float32)
+    l4 = ((l + 3) // 4) * 4
+    y = np.zeros((n, l4), dtype=np.float32)
+    y[:, :l] = rng.standard_normal((n, l)).astype(np.float32)
+    mean = x.mean(axis=0).astype(np.float32)
+    ref = (x.astype(np.float64) - mean.astype(np.float64)).T @ y.astype(np.float64)
+    ctx = pd.default_context()
+    outs = {}
+    for eng in (0, 1):
+        ctx.set_f32_engine(eng)
+        outs[eng] = pd.xty(x, y, mean)
+    ctx.set_f32_engine(1)
+    scale = np.abs(ref).max() + np.sqrt(n)
+    assert np.max(np.abs(outs[0] - ref)) < 1e-5 * scale
+    assert np.max(np.abs(outs[1] - ref)) < 1e-5 * scale
