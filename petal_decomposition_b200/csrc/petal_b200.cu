@@ -383,7 +383,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     const double cutoff = rank_cutoff<T>();
 
     // Y = Xc * Omega (src/pca.rs:707), fused with ||Xc||_F^2 (src/pca.rs:533)
-    const int64_t ly = ((l + 3) / 4) * 4;  // row pitch of Y: 16 B multiple so TMA can stream it
+    const int64_t ly = ((l + 15) / 16) * 16;  // row pitch of Y: whole 64 B chunks (TMA reads, vector epilogue stores)
     DBuf<T> Y(ctx, (size_t)(n * ly));
     DBuf<double> small(ctx, (size_t)(l * l + d * l + 1));  // [G2 | C' | tv] reduced together
     double* G2 = small.p;

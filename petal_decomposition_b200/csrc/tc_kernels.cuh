@@ -25,12 +25,14 @@
 namespace petal {
 namespace tc {
 
-constexpr int kThreads = 384;
-constexpr int kTransformWarps = 8;
+constexpr int kTransformWarps = 16;          // two warps per 32 TMEM lanes: each owns one half (16 values) of a K block
+constexpr int kEpilogueWarps = 8;            // tc_atb: only the first half keeps the register accumulators
+constexpr int kThreads = (kTransformWarps + 4) * 32;  // + TMA, MMA, TMEM-alloc, spare
 constexpr int kMT = 2;            // M tiles (128 TMEM lanes each) per CTA
 constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
 constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
 constexpr int kTmemCols = 512;
+constexpr int kYBufs = 3;         // tc_atb: ring of transposed Y tiles (decoupled from the 2 TMEM operand stages)
 constexpr int kAStageCols = kMT * 64;  // per TMEM operand stage: MT x (32 hi + 32 lo) columns
 constexpr int kAccBase = 2 * kAStageCols;  // accumulators start after the two operand stages (256)
 
@@ -68,6 +70,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             __trap();
         }
     }
+}
+// true in exactly one (elected) lane of a fully converged warp; keeps the surrounding code warp-uniform so
+// that descriptors / addresses live in uniform registers (the tensor-core issue path reads those)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -116,6 +125,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -125,6 +142,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+// 16 lanes x 16 columns: thread t holds (lane t/4, cols 2(t%4)+{0,1}) in v[0..1], (lane t/4+8, same cols) in
+// v[2..3], and the same two rows for cols 8+2(t%4)+{0,1} in v[4..5] / v[6..7]  -> 4 lanes cover one 32 B sector
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -171,6 +196,7 @@ struct TcParams {
     int64_t slice_rows;   // rows per CTA slice (multiple of 32)
     int fgroups;          // feature groups of 256
     int dbg;
+    long long* trace;     // optional timeline trace (PETAL_TC_TRACE), [role][event][kblock]
 };
 
 struct SmemLayout {
@@ -184,7 +210,7 @@ __host__ __device__ inline SmemLayout make_layout(bool atb, int n_pad, int stage
     l.stage_x = kXStageBytes;
     l.stage_b = (uint32_t)n_pad * 128u;   // tc_xb: B^T tile [n_pad][32]; tc_atb: raw Y tile [32][n_pad]
     l.stage_mu = 128;
-    l.ylo_bytes = atb ? 2u * (uint32_t)n_pad * 128u : 0u;  // tc_atb: K-major Y_hi | Y_lo tiles [n_pad][32]
+    l.ylo_bytes = atb ? 2u * (uint32_t)n_pad * 128u : 0u;  // tc_atb: K-major Y_hi | Y_lo tiles [n_pad][32], ring of kYBufs
     uint32_t off = 0;
     l.x = off;
     off += (uint32_t)stages * l.stage_x;
@@ -193,7 +219,7 @@ __host__ __device__ inline SmemLayout make_layout(bool atb, int n_pad, int stage
     l.blo = off;
     off += atb ? 0u : (uint32_t)stages * l.stage_b;
     l.ylo = off;
-    off += 2u * l.ylo_bytes;
+    off += (uint32_t)kYBufs * l.ylo_bytes;
     l.mu = off;
     off += atb ? 0u : (uint32_t)stages * l.stage_mu;
     l.bars = off;
@@ -217,6 +243,7 @@ __device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return b
 __device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (24 + (uint32_t)t); }
 __device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (26 + (uint32_t)t); }
 __device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 28; }
+__device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }
 __device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 29; }
 
 // ------------------------------------------------------------------------------------------
@@ -231,6 +258,12 @@ __device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base +
 //           chain is cut every chunk: the epilogue adds the chunk result into fp32 registers
 //           (round-to-nearest) and only the CTA's final sums go to global memory (f64 atomics).
 // ------------------------------------------------------------------------------------------
+constexpr int kTraceKB = 512;   // K blocks traced (CTA 0 only)
+constexpr int kTraceEvents = 8;
+__device__ __forceinline__ void trace_ev(const TcParams& p, int ev, uint32_t it) {
+    if (p.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceKB) p.trace[ev * kTraceKB + it] = clock64();
+}
+
 struct Group {
     int64_t row0;
     int64_t kblocks;
@@ -265,6 +298,214 @@ __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.syn
 template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// transform + epilogue role (warps 0 .. 15).  warp w: M tile (w >> 2) & 1, TMEM lane quarter w & 3,
+// K-block half w >> 3.  EPI: this warp also runs the epilogue (tc_xb: all; tc_atb: first half only -
+// they hold the register accumulators, hence the separate instantiation and register budget).
+template <bool ATB, int NP, bool EPI>
+__device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_ptr, const SmemLayout& L,
+                                               uint32_t bars, uint32_t tmem_base, int warp, int lane, int n_pad,
+                                               int S) {
+    {
+        const int half = warp >> 3;
+        constexpr bool epi = EPI;  // warps that run the epilogue
+        const int mt = (warp >> 2) & 1;
+        const int q = warp & 3;
+        const int lrow = q * 32 + lane;           // lane (= row / feature) inside the M tile
+        const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+        const int ttid = threadIdx.x;             // 0 .. 511
+        uint32_t it = 0;
+        double ss = 0.0;
+        float racc[(ATB && EPI) ? NP : 1];
+#pragma unroll
+        for (int j = 0; j < ((ATB && EPI) ? NP : 1); ++j) racc[j] = 0.f;
+        // tc_atb: this thread's share of the Y-tile transposition (loop invariant): chunk i covers
+        // column nn = i % n_pad, K rows 4*cc .. 4*cc+3 with cc = i / n_pad
+        constexpr int kYIter = ATB ? (NP * 8 + kTransformWarps * 32 - 1) / (kTransformWarps * 32) : 1;
+        int y_src[kYIter], y_dst[kYIter];
+        if (ATB) {
+#pragma unroll
+            for (int u = 0; u < kYIter; ++u) {
+                const int i = ttid + u * kTransformWarps * 32;
+                const int nn = i % n_pad, cc = i / n_pad;
+                y_src[u] = (i < n_pad * 8) ? (cc * 4 * n_pad + nn) : -1;
+                y_dst[u] = nn * 128 + ((cc ^ (nn & 7)) << 4);
+            }
+        }
+        Group g;
+        g.f0 = 0;
+        for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
+            float mu_f = 0.f;
+            if (ATB) mu_f = p.mu_pad[g.f0 + mt * 128 + lrow];
+            const bool row_valid = ATB ? true : (g.row0 + mt * 128 + lrow < p.n);
+            float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
+            for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                const int s = (int)(it % (uint32_t)S);
+                const uint32_t ph = (it / (uint32_t)S) & 1u;
+                const int ta = (int)(it & 1u);
+                const uint32_t pa = (it >> 1) & 1u;
+                mbar_wait(bar_full(bars, s), ph);
+                if (warp == 0 && lane == 0) trace_ev(p, 3, it);
+                uint32_t v[16];
+                const uint8_t* xs = base_ptr + L.x + (uint32_t)s * L.stage_x;
+                if (ATB) {
+                    // tile [32 rows][256 features] row-major: this thread owns one feature (transpose)
+                    // and the K rows 16*half .. 16*half+15
+                    const float* xf = reinterpret_cast<const float*>(xs) + (half * 16) * 256 + mt * 128 + lrow;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(xf[k * 256] - mu_f);
+                } else {
+                    // tile [256 rows][32 floats], 128 B rows, SWIZZLE_128B: this thread owns one row and
+                    // the 16 B chunks 4*half .. 4*half+3 of it
+                    const int r = mt * 128 + lrow;
+                    const uint8_t* xr = xs + r * 128;
+                    const float4* mus = reinterpret_cast<const float4*>(base_ptr + L.mu + (uint32_t)s * L.stage_mu);
+#pragma unroll
+                    for (int cq = 0; cq < 4; ++cq) {
+                        const int c = half * 4 + cq;
+                        float4 x4 = *reinterpret_cast<const float4*>(xr + ((c ^ (r & 7)) << 4));
+                        float4 m = mus[c];
+                        float e0 = x4.x - m.x, e1 = x4.y - m.y, e2 = x4.z - m.z, e3 = x4.w - m.w;
+                        v[cq * 4 + 0] = __float_as_uint(e0);
+                        v[cq * 4 + 1] = __float_as_uint(e1);
+                        v[cq * 4 + 2] = __float_as_uint(e2);
+                        v[cq * 4 + 3] = __float_as_uint(e3);
+                        if (p.sumsq) {
+                            ss0 += e0 * e0;
+                            ss1 += e1 * e1;
+                            ss2 += e2 * e2;
+                            ss3 += e3 * e3;
+                        }
+                    }
+                    __syncwarp();  // smem X stage consumed (values are in registers)
+                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
+                }
+                if (ATB) {
+                    // B operand of this K block: raw Y tile [32 rows][n_pad] (row-major) -> transposed
+                    // K-major tiles Y_hi / Y_lo [n_pad][32 rows] with the 128 B swizzle the MMA expects.
+                    const float* yr = reinterpret_cast<const float*>(base_ptr + L.bhi + (uint32_t)s * L.stage_b);
+                    const int yb = (int)(it % (uint32_t)kYBufs);
+                    mbar_wait(bar_y_free(bars, yb), ((it / (uint32_t)kYBufs) & 1u) ^ 1u);  // MMAs of K block it-3 done
+                    uint8_t* bh = base_ptr + L.ylo + (uint32_t)yb * L.ylo_bytes;
+                    uint8_t* bl = bh + n_pad * 128;
+#pragma unroll
+                    for (int u = 0; u < kYIter; ++u) {
+                        if (y_src[u] < 0) continue;
+                        const float* ys = yr + y_src[u];
+                        float4 h, l4;
+                        h.x = ys[0];
+                        h.y = ys[n_pad];
+                        h.z = ys[2 * n_pad];
+                        h.w = ys[3 * n_pad];
+                        l4.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u);
+                        l4.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u);
+                        l4.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u);
+                        l4.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4*>(bh + y_dst[u]) = h;
+                        *reinterpret_cast<float4*>(bl + y_dst[u]) = l4;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));  // X and raw Y stage consumed
+                }
+                // TMEM operand stage `ta` must have been drained by the MMAs of two K blocks ago
+                if (warp == 0 && lane == 0) trace_ev(p, 4, it);
+                mbar_wait(bar_a_free(bars, ta), pa ^ 1u);
+                tc_fence_after();
+                if (warp == 0 && lane == 0) trace_ev(p, 5, it);
+                const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kAStageCols + mt * 64 + half * 16);
+                tmem_st16(a_addr, v);  // hi: the tensor core ignores the low 13 mantissa bits
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float f = __uint_as_float(v[k]);
+                    v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
+                }
+                tmem_st16(a_addr + 32u, v);  // lo = v - tf32(v), exact
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_a_ready(bars, ta));
+                if (warp == 0 && lane == 0) trace_ev(p, 6, it);
+            }
+            if (!ATB && row_valid) ss += (double)((ss0 + ss1) + (ss2 + ss3));
+
+            // ---------------- epilogue for this group ----------------
+            if constexpr (epi) {
+                mbar_wait(bar_acc_full(bars), (uint32_t)gi & 1u);
+                tc_fence_after();
+                const uint32_t acc = tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad);
+                if constexpr (ATB && EPI) {
+#pragma unroll
+                    for (int c0 = 0; c0 < NP; c0 += 16) {
+                        uint32_t w[16];
+                        tmem_ld16(acc + (uint32_t)c0, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) racc[c0 + j] += __uint_as_float(w[j]);
+                    }
+                } else if constexpr (!ATB) {
+                    // Each warp of a lane-quarter pair drains 16 of the 32 lanes with the 16x256b pattern:
+                    // four lanes hold 8 consecutive columns of one row, so every store instruction writes
+                    // whole 32 B sectors (8 rows x 32 B).
+                    const int t0 = lane & 3, t1 = lane >> 2;
+                    const uint32_t acc16 = tmem_base + ((uint32_t)(q * 32 + half * 16) << 16) +
+                                           (uint32_t)(kAccBase + mt * n_pad);
+                    const int64_t ra = g.row0 + mt * 128 + q * 32 + half * 16 + t1;
+                    const int64_t rb = ra + 8;
+                    for (int c0 = 0; c0 < n_pad; c0 += 16) {
+                        uint32_t w[8];
+                        tmem_ld_16x256b_x2(acc16 + (uint32_t)c0, w);
+                        tmem_ld_wait();
+                        const int ca = c0 + 2 * t0, cb = ca + 8;
+                        if (p.y_vec) {
+                            if (ra < p.n) {
+                                if (ca + 1 < p.ldy)
+                                    *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) =
+                                        make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
+                                if (cb + 1 < p.ldy)
+                                    *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) =
+                                        make_float2(__uint_as_float(w[4]), __uint_as_float(w[5]));
+                            }
+                            if (rb < p.n) {
+                                if (ca + 1 < p.ldy)
+                                    *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) =
+                                        make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
+                                if (cb + 1 < p.ldy)
+                                    *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) =
+                                        make_float2(__uint_as_float(w[6]), __uint_as_float(w[7]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const int64_t r = (e & 2) ? rb : ra;
+                                const int c = ((e & 4) ? cb : ca) + (e & 1);
+                                if (r < p.n && c < p.ldy) p.Y[r * p.ldy + c] = __uint_as_float(w[e]);
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(bars));
+            }
+        }
+        if constexpr (ATB) {
+            if constexpr (EPI) {
+                // the CTA's partial (256 features x L) -> global f64 accumulator
+                const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
+                if (f < p.K) {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j)
+                        if (j < p.L) atomicAdd(&p.Z[f * p.ldz + j], (double)racc[j]);
+                }
+            }
+        } else if (p.sumsq) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0) atomicAdd(p.sumsq, ss);
+        }
+    }
+}
+
 template <bool ATB, int NP>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -280,17 +521,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full(bars, s), 1);
             mbar_init(bar_empty_x(bars, s), kTransformWarps);
-            mbar_init(bar_empty_b(bars, s), 1);
+            mbar_init(bar_empty_b(bars, s), kMT);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_a_ready(bars, t), kTransformWarps);
-            mbar_init(bar_a_free(bars, t), 1);
+            mbar_init(bar_a_free(bars, t), kMT);
         }
-        mbar_init(bar_acc_full(bars), 1);
-        mbar_init(bar_acc_empty(bars), kTransformWarps);
+        mbar_init(bar_acc_full(bars), kMT);
+        for (int t = 0; t < kYBufs; ++t) mbar_init(bar_y_free(bars, t), kMT);
+        mbar_init(bar_acc_empty(bars), ATB ? kEpilogueWarps : kTransformWarps);
         fence_barrier_init();
     }
-    if (warp == 10) tmem_alloc(base + L.tmem_slot, kTmemCols);
+    if (warp == kTransformWarps + 3) tmem_alloc(base + L.tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -298,8 +540,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const uint32_t stage_tx = ATB ? (L.stage_x + L.stage_b) : (L.stage_x + 2u * L.stage_b + L.stage_mu);
 
     if (warp >= kTransformWarps) {
-        if (ATB) reg_dealloc<56>();
-        if (warp == 8) {
+        if (ATB) reg_dealloc<40>();
+        if (warp == kTransformWarps) {
             // ================================ TMA producer ================================
             if (lane == 0) {
                 uint32_t it = 0;
@@ -310,6 +552,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         const uint32_t ph = (it / (uint32_t)S) & 1u;
                         mbar_wait(bar_empty_x(bars, s), ph ^ 1u);
                         if (!ATB) mbar_wait(bar_empty_b(bars, s), ph ^ 1u);
+                        trace_ev(p, 0, it);
                         const uint32_t full = bar_full(bars, s);
                         mbar_expect_tx(full, stage_tx);
                         if (ATB) {
@@ -326,205 +569,79 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     }
                 }
             }
-        } else if (warp == 9) {
-            // ================================ MMA issuer ================================
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc_tf32(n_pad, 0);
-                uint32_t it = 0;
-                Group g;
-                for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
-                    mbar_wait(bar_acc_empty(bars), ((uint32_t)gi & 1u) ^ 1u);
+        } else if (warp == kTransformWarps + 1 || warp == kTransformWarps + 2) {
+            // ================================ MMA issuers ================================
+            // One warp per M tile (two independent issue streams).  The whole warp runs the loop so that
+            // every address / descriptor is warp-uniform; only the tcgen05 instructions are elected.
+            const int mt = warp - (kTransformWarps + 1);
+            const uint32_t idesc = make_idesc_tf32(n_pad, 0);
+            const uint32_t acc = tmem_base + (uint32_t)(kAccBase + mt * n_pad);
+            uint32_t it = 0;
+            Group g;
+            for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
+                mbar_wait(bar_acc_empty(bars), ((uint32_t)gi & 1u) ^ 1u);
+                tc_fence_after();
+                for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                    const int s = (int)(it % (uint32_t)S);
+                    const uint32_t ph = (it / (uint32_t)S) & 1u;
+                    const int ta = (int)(it & 1u);
+                    const uint32_t pa = (it >> 1) & 1u;
+                    // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are produced
+                    // by the transform warps together with the TMEM operand (a_ready covers both)
+                    if (!ATB) mbar_wait(bar_full(bars, s), ph);
+                    mbar_wait(bar_a_ready(bars, ta), pa);
                     tc_fence_after();
-                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
-                        const int s = (int)(it % (uint32_t)S);
-                        const uint32_t ph = (it / (uint32_t)S) & 1u;
-                        const int ta = (int)(it & 1u);
-                        const uint32_t pa = (it >> 1) & 1u;
-                        // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are produced
-                        // by the transform warps together with the TMEM operand (a_ready covers both)
-                        if (!ATB) mbar_wait(bar_full(bars, s), ph);
-                        mbar_wait(bar_a_ready(bars, ta), pa);
-                        tc_fence_after();
-                        // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
-                        const uint32_t bhi_addr = ATB ? (base + L.ylo + (uint32_t)ta * L.ylo_bytes)
-                                                      : (base + L.bhi + (uint32_t)s * L.stage_b);
-                        const uint32_t blo_addr = ATB ? (bhi_addr + (uint32_t)n_pad * 128u)
-                                                      : (base + L.blo + (uint32_t)s * L.stage_b);
+                    if (mt == 0 && lane == 0) trace_ev(p, 1, it);
+                    // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
+                    const int yb = (int)(it % (uint32_t)kYBufs);
+                    const uint32_t bhi_addr = ATB ? (base + L.ylo + (uint32_t)yb * L.ylo_bytes)
+                                                  : (base + L.bhi + (uint32_t)s * L.stage_b);
+                    const uint32_t blo_addr = ATB ? (bhi_addr + (uint32_t)n_pad * 128u)
+                                                  : (base + L.blo + (uint32_t)s * L.stage_b);
+                    const uint64_t dhi0 = make_desc_sw128(bhi_addr, 16u, 1024u);
+                    const uint64_t dlo0 = make_desc_sw128(blo_addr, 16u, 1024u);
+                    const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kAStageCols + mt * 64);
+                    if (elect_one()) {
 #pragma unroll
-                        for (int mt = 0; mt < kMT; ++mt) {
-                            const uint32_t acc = tmem_base + (uint32_t)(kAccBase + mt * n_pad);
-                            const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kAStageCols + mt * 64);
-#pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                // 32 B per K step inside the 128 B swizzle row
-                                const uint64_t dhi = make_desc_sw128(bhi_addr + (uint32_t)ks * 32u, 16u, 1024u);
-                                const uint64_t dlo = make_desc_sw128(blo_addr + (uint32_t)ks * 32u, 16u, 1024u);
-                                const uint32_t a_hi = a_hi0 + (uint32_t)ks * 8u;
-                                const uint32_t a_lo = a_hi + 32u;
-                                mma_tf32_ts(acc, a_lo, dhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                                mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
-                                mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
-                            }
+                        for (int ks = 0; ks < 4; ++ks) {
+                            // 32 B (= 2 descriptor address units) per K step inside the 128 B swizzle row
+                            const uint64_t dhi = dhi0 + (uint64_t)(ks * 2);
+                            const uint64_t dlo = dlo0 + (uint64_t)(ks * 2);
+                            const uint32_t a_hi = a_hi0 + (uint32_t)ks * 8u;
+                            const uint32_t a_lo = a_hi + 32u;
+                            mma_tf32_ts(acc, a_lo, dhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
+                            mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
                         }
                         tc_commit(bar_a_free(bars, ta));
                         if (!ATB) tc_commit(bar_empty_b(bars, s));
+                        else tc_commit(bar_y_free(bars, yb));
                     }
-                    tc_commit(bar_acc_full(bars));
+                    __syncwarp();
+                    if (mt == 0 && lane == 0) trace_ev(p, 2, it);
                 }
+                if (elect_one()) tc_commit(bar_acc_full(bars));
+                __syncwarp();
             }
         }
     } else {
         // ================================ transform + epilogue ================================
-        if (ATB) reg_alloc<208>();
-        const int mt = warp >> 2;                 // M tile
-        const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int lrow = q * 32 + lane;           // lane (= row / feature) inside the M tile
-        const uint32_t lane_field = (uint32_t)(q * 32) << 16;
-        uint32_t it = 0;
-        double ss = 0.0;
-        float racc[ATB ? NP : 1];
-#pragma unroll
-        for (int j = 0; j < (ATB ? NP : 1); ++j) racc[j] = 0.f;
-        Group g;
-        g.f0 = 0;
-        for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
-            float mu_f = 0.f;
-            if (ATB) mu_f = p.mu_pad[g.f0 + mt * 128 + lrow];
-            const bool row_valid = ATB ? true : (g.row0 + mt * 128 + lrow < p.n);
-            float ssf = 0.f;
-            for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
-                const int s = (int)(it % (uint32_t)S);
-                const uint32_t ph = (it / (uint32_t)S) & 1u;
-                const int ta = (int)(it & 1u);
-                const uint32_t pa = (it >> 1) & 1u;
-                mbar_wait(bar_full(bars, s), ph);
-                uint32_t v[32];
-                const uint8_t* xs = base_ptr + L.x + (uint32_t)s * L.stage_x;
-                if (ATB) {
-                    // tile [32 rows][256 features] row-major: this thread owns one feature (transpose)
-                    const float* xf = reinterpret_cast<const float*>(xs) + mt * 128 + lrow;
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(xf[k * 256] - mu_f);
-                } else {
-                    // tile [256 rows][32 floats], 128 B rows, SWIZZLE_128B: this thread owns one row
-                    const int r = mt * 128 + lrow;
-                    const uint8_t* xr = xs + r * 128;
-                    const float4* mus = reinterpret_cast<const float4*>(base_ptr + L.mu + (uint32_t)s * L.stage_mu);
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float4 x4 = *reinterpret_cast<const float4*>(xr + ((c ^ (r & 7)) << 4));
-                        float4 m = mus[c];
-                        float e[4] = {x4.x - m.x, x4.y - m.y, x4.z - m.z, x4.w - m.w};
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            v[c * 4 + j] = __float_as_uint(e[j]);
-                            ssf += e[j] * e[j];
-                        }
-                    }
-                    __syncwarp();  // smem X stage consumed (values are in registers)
-                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
-                }
-                // TMEM operand stage `ta` must have been drained by the MMAs of two K blocks ago
-                mbar_wait(bar_a_free(bars, ta), pa ^ 1u);
-                tc_fence_after();
-                const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kAStageCols + mt * 64);
-                tmem_st32(a_addr, v);  // hi: the tensor core ignores the low 13 mantissa bits
-#pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float f = __uint_as_float(v[k]);
-                    v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
-                }
-                tmem_st32(a_addr + 32u, v);  // lo = v - tf32(v), exact
-                if (ATB) {
-                    // B operand of this K block: raw Y tile [32 rows][n_pad] (row-major) -> transposed
-                    // K-major tiles Y_hi / Y_lo [n_pad][32 rows] with the 128 B swizzle the MMA expects.
-                    const float* yr = reinterpret_cast<const float*>(base_ptr + L.bhi + (uint32_t)s * L.stage_b);
-                    uint8_t* bh = base_ptr + L.ylo + (uint32_t)ta * L.ylo_bytes;
-                    uint8_t* bl = bh + n_pad * 128;
-                    const int nwork = n_pad * 8;  // one 16 B chunk (4 K values of one column) each
-                    for (int i = threadIdx.x; i < nwork; i += kTransformWarps * 32) {
-                        const int nn = i % n_pad, cc = i / n_pad;
-                        float4 h, l4;
-                        h.x = yr[(cc * 4 + 0) * n_pad + nn];
-                        h.y = yr[(cc * 4 + 1) * n_pad + nn];
-                        h.z = yr[(cc * 4 + 2) * n_pad + nn];
-                        h.w = yr[(cc * 4 + 3) * n_pad + nn];
-                        l4.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u);
-                        l4.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u);
-                        l4.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u);
-                        l4.w = h.w - __uint_as_float(__float_as_uint(h.w) & 0xFFFFE000u);
-                        const int off = nn * 128 + ((cc ^ (nn & 7)) << 4);
-                        *reinterpret_cast<float4*>(bh + off) = h;
-                        *reinterpret_cast<float4*>(bl + off) = l4;
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));  // X and raw Y stage consumed
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_a_ready(bars, ta));
-            }
-            if (!ATB && row_valid) ss += (double)ssf;
-
-            // ---------------- epilogue for this group ----------------
-            mbar_wait(bar_acc_full(bars), (uint32_t)gi & 1u);
-            tc_fence_after();
-            const uint32_t acc = tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad);
-            if (ATB) {
-#pragma unroll
-                for (int c0 = 0; c0 < NP; c0 += 16) {
-                    uint32_t w[16];
-                    tmem_ld16(acc + (uint32_t)c0, w);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) racc[c0 + j] += __uint_as_float(w[j]);
-                }
-            } else {
-                const int64_t r = g.row0 + mt * 128 + lrow;
-                for (int c0 = 0; c0 < n_pad; c0 += 16) {
-                    uint32_t w[16];
-                    tmem_ld16(acc + (uint32_t)c0, w);
-                    tmem_ld_wait();
-                    if (r < p.n) {
-                        float* yr = p.Y + r * p.ldy + c0;
-                        if (p.y_vec && c0 + 16 <= p.ldy) {
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4)
-                                *reinterpret_cast<float4*>(yr + j) =
-                                    make_float4(__uint_as_float(w[j]), __uint_as_float(w[j + 1]),
-                                                __uint_as_float(w[j + 2]), __uint_as_float(w[j + 3]));
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < p.ldy) yr[j] = __uint_as_float(w[j]);
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc_empty(bars));
-        }
         if (ATB) {
-            // the CTA's partial (256 features x L) -> global f64 accumulator
-            const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
-            if (f < p.K) {
-#pragma unroll
-                for (int j = 0; j < NP; ++j)
-                    if (j < p.L) atomicAdd(&p.Z[f * p.ldz + j], (double)racc[j]);
+            if (warp < kEpilogueWarps) {
+                reg_alloc<144>();
+                transform_role<ATB, NP, true>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
+            } else {
+                reg_dealloc<72>();
+                transform_role<ATB, NP, false>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
             }
-        } else if (p.sumsq) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-            if (lane == 0) atomicAdd(p.sumsq, ss);
+        } else {
+            transform_role<ATB, NP, true>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 10) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kTransformWarps + 3) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -598,8 +715,32 @@ inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t sm
         PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
-    tc_gemm_kernel<ATB, NP><<<grid, kThreads, smem, ctx->stream>>>(p);
+    const char* trace_path = getenv("PETAL_TC_TRACE");
+    if (trace_path == nullptr) {
+        tc_gemm_kernel<ATB, NP><<<grid, kThreads, smem, ctx->stream>>>(p);
+        check_launch(ctx);
+        return;
+    }
+    // debug: record a clock64 timeline of CTA 0 and append it to the file
+    TcParams q = p;
+    const size_t cnt = (size_t)kTraceEvents * kTraceKB;
+    DBuf<long long> tr(ctx, cnt);
+    tr.zero();
+    q.trace = tr.p;
+    tc_gemm_kernel<ATB, NP><<<grid, kThreads, smem, ctx->stream>>>(q);
     check_launch(ctx);
+    std::vector<long long> h(cnt);
+    PETAL_CUDA(cudaMemcpyAsync(h.data(), tr.p, cnt * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    FILE* f = fopen(trace_path, "a");
+    if (f) {
+        fprintf(f, "kernel atb=%d np=%d n=%lld K=%lld n_pad=%d grid=%d\n", (int)ATB, NP, (long long)p.n, (long long)p.K, p.n_pad, grid);
+        for (int e = 0; e < kTraceEvents; ++e) {
+            for (int i = 0; i < kTraceKB; ++i) fprintf(f, "%lld ", h[(size_t)e * kTraceKB + i]);
+            fprintf(f, "\n");
+        }
+        fclose(f);
+    }
 }
 
 // Y[n x ldy] = (A - mu) * B.  B: TS in {float, double}, K x L row-major (ldb) or L x K when b_trans.
