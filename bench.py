@@ -349,6 +349,7 @@ def main():
             xh = xh_t.numpy()
             del x
             torch.cuda.empty_cache()
+            ctx.trim()
             for _ in range(min(args.warmup, 1)):
                 step(xh)
             barrier()

@@ -53,6 +53,8 @@ const char* petal_last_error(const petal_ctx* ctx);
 const char* petal_last_global_error(void);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the internal one. */
 int petal_ctx_set_stream(petal_ctx* ctx, void* cuda_stream);
+/* Workspaces are kept in a stream-ordered pool between calls; this returns them to the driver. */
+int petal_ctx_trim(petal_ctx* ctx);
 /* Blocks until all work queued by this context has finished. */
 int petal_ctx_synchronize(petal_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */

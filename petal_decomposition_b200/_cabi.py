@@ -32,6 +32,7 @@ SYMBOLS = {
     "petal_last_global_error": (C.c_char_p, []),
     "petal_ctx_set_stream": (c_int, [c_vp, c_vp]),
     "petal_ctx_synchronize": (c_int, [c_vp]),
+    "petal_ctx_trim": (c_int, [c_vp]),
     "petal_ctx_launch_count": (c_i64, [c_vp]),
     "petal_ctx_set_f32_engine": (c_int, [c_vp, c_int]),
     "petal_ctx_set_profiling": (c_int, [c_vp, c_int]),

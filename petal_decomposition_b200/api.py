@@ -78,6 +78,10 @@ class Context:
     def synchronize(self):
         self.check(self.lib.petal_ctx_synchronize(self.handle))
 
+    def trim(self):
+        """Returns the pooled workspaces to the driver."""
+        self.check(self.lib.petal_ctx_trim(self.handle))
+
     def launch_count(self) -> int:
         return int(self.lib.petal_ctx_launch_count(self.handle))
 

@@ -273,7 +273,7 @@ void orthonormalize_columns(petal_ctx* ctx, double* Z, int64_t rows, int64_t l, 
 // max-|.| entry of the score column (same sign as the U column since sigma >= 0), first row
 // wins, across all ranks; flips score columns and component rows.
 template <typename T>
-void flip_signs(petal_ctx* ctx, T* scores, int64_t n, int64_t k, T* comps, int64_t d) {
+void flip_signs(petal_ctx* ctx, T* scores, int64_t n, int64_t k, T* comps, int64_t d, bool scores_wanted = true) {
     if (k == 0) return;
     DBuf<double> local3(ctx, (size_t)(k * 3));
     launch_colabsmax<T>(ctx, scores, n, k, k, local3.p);
@@ -287,12 +287,35 @@ void flip_signs(petal_ctx* ctx, T* scores, int64_t n, int64_t k, T* comps, int64
         launch1(ctx);
         flip3 = out3.p;
     }
-    launch_apply_flip<T>(ctx, scores, n, k, k, comps, d, flip3);
+    launch_apply_flip<T>(ctx, scores_wanted ? scores : nullptr, n, k, k, comps, d, flip3);
 }
 
 void finish_call(petal_ctx* ctx, bool any_host_output) {
     if (any_host_output) PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
 }
+
+// debug aid: PETAL_PHASES=1 prints host wall time per phase (synchronising after each)
+struct PhaseClock {
+    petal_ctx* ctx;
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    explicit PhaseClock(petal_ctx* c) : ctx(c), on(getenv("PETAL_PHASES") != nullptr), t0(0) {
+        if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); }
+    }
+    void mark(const char* label) {
+        if (!on) return;
+        double t1 = now();
+        cudaStreamSynchronize(ctx->stream);
+        double t2 = now();
+        fprintf(stderr, "[petal phase] %-28s host %8.3f ms  (+%8.3f ms waiting for the device)\n", label, t1 - t0, t2 - t1);
+        t0 = now();
+    }
+};
 
 std::string dim_message(int64_t k) { return "every dimension should be at least " + std::to_string(k); }
 
@@ -341,7 +364,7 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
             scores_dev = scores_tmp.p;
         }
         gemm_xb<T>(ctx, X.p, d, n, d, comps_dev, d, true, k, cm.mu, nullptr, scores_dev, k);
-        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d);
+        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores);
         if (sing) {
             sqrt_cast_kernel<T><<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(lam.p, k, sing.p);
             launch1(ctx);
@@ -373,6 +396,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     const int64_t l = std::min<int64_t>(l_full, std::min<int64_t>(n_total, d));
     if (l == 0) return;
 
+    PhaseClock pc(ctx);
     DevIn<T> X(ctx, x_user, (size_t)(n * d));
     DevIn<T> Omega(ctx, omega_user, (size_t)(d * l_full));
     DevOut<T> comps(ctx, comps_u, (size_t)(k * d)), mean(ctx, mean_u, (size_t)d), sing(ctx, sing_u, (size_t)k),
@@ -381,6 +405,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     ColMean<T> cm;
     compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
     const double cutoff = rank_cutoff<T>();
+    pc.mark("stage inputs + mean");
 
     // Y = Xc * Omega (src/pca.rs:707), fused with ||Xc||_F^2 (src/pca.rs:533)
     const int64_t ly = ((l + 15) / 16) * 16;  // row pitch of Y: whole 64 B chunks (TMA reads, vector epilogue stores)
@@ -392,13 +417,17 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     PETAL_CUDA(cudaMemsetAsync(tvd, 0, sizeof(double), ctx->stream));
     gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
 
+    pc.mark("Y = Xc Omega");
     // power iterations (src/pca.rs:708-715): Z = Xc^T Y, re-orthonormalise, Y = Xc Z
     DBuf<double> Zd(ctx, (size_t)(d * l));
     for (int64_t it = 0; it < n_iter; ++it) {
         gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, ly, l, nullptr, n, Zd.p);
         allreduce_sum(ctx, Zd.p, (size_t)(d * l));
+        pc.mark("  Z = Xc^T Y");
         orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
+        pc.mark("  orth(Z)");
         gemm_xb_b64<T>(ctx, X.p, d, n, d, Zd.p, l, l, cm.mu, Y.p, ly);
+        pc.mark("  Y = Xc Z");
     }
 
     // thin QR of Y (src/pca.rs:716) done implicitly in two Gram rounds (CholeskyQR2-style, with a
@@ -409,11 +438,14 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     gemm_atb<T>(ctx, Y.p, ly, l, nullptr, Y.p, ly, l, nullptr, n, G1.p);
     allreduce_sum(ctx, G1.p, (size_t)(l * l));
     gram_to_orthonormalizer(ctx, G1.p, l, cutoff, kGramNoise, P.p);
+    pc.mark("G1 = Y^T Y, P1");
     gemm_xb_b64<T>(ctx, Y.p, ly, n, l, P.p, l, l, nullptr, Y1.p, ly);
+    pc.mark("Y1 = Y P1");
     // B = Q^T Xc (src/pca.rs:681) = P2^T (Y1^T Xc):  C' = Xc^T Y1 (d x l) in one pass over X
     gemm_atb<T>(ctx, Y1.p, ly, l, nullptr, Y1.p, ly, l, nullptr, n, G2);
     gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, ly, l, nullptr, n, Cp);
     allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
+    pc.mark("G2, C' = Xc^T Y1");
     gram_to_orthonormalizer(ctx, G2, l, 1e-6, kGramNoise, P.p);  // P2 (l x l)
     DBuf<double> M1(ctx, (size_t)(d * l)), Bm(ctx, (size_t)(l * d));
     gemm_xb<double>(ctx, Cp, l, d, l, P.p, l, false, l, nullptr, nullptr, M1.p, l);
@@ -442,6 +474,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         }
     }
     launch_normalize_rows(ctx, Bout.p, sigB.p, l, d, 0.0, Vt.p);
+    pc.mark("small SVD of B");
 
     DBuf<T> comps_tmp;
     T* comps_dev = comps.p;
@@ -464,7 +497,9 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
             scores_dev = scores_tmp.p;
         }
         gemm_xb_b64<T>(ctx, Y1.p, ly, n, l, S.p, k, k, nullptr, scores_dev, k);
-        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d);  // svd_flip, src/pca.rs:684
+        pc.mark("scores = Y1 S");
+        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores);  // svd_flip, src/pca.rs:684
+        pc.mark("svd_flip");
         if (sing) launch_cast<double, T>(ctx, sigB.p, sing.p, k);
     }
     if (mean) launch_cast<T, T>(ctx, cm.mean_t.p, mean.p, d);
@@ -660,7 +695,9 @@ int petal_ctx_create(int device, petal_ctx** out) {
         PETAL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t thresh = (uint64_t)8 << 30;
+            // keep freed workspaces in the stream-ordered pool: a fit re-uses multi-GB buffers (Y, scores)
+            // every call and returning them to the driver costs tens of ms (petal_ctx_trim releases them)
+            uint64_t thresh = UINT64_MAX;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
         }
         *out = ctx;
@@ -691,6 +728,15 @@ int petal_ctx_set_stream(petal_ctx* ctx, void* cuda_stream) {
         if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
         ctx->stream = static_cast<cudaStream_t>(cuda_stream);
         ctx->own_stream = false;
+    });
+}
+
+int petal_ctx_trim(petal_ctx* ctx) {
+    return guarded(ctx, [&] {
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaMemPool_t pool;
+        PETAL_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        PETAL_CUDA(cudaMemPoolTrimTo(pool, 0));
     });
 }
 

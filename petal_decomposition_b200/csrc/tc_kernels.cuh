@@ -776,7 +776,7 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     const SmemLayout lay = make_layout(false, n_pad, stages);
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
-    KTimer kt(ctx, "tc_xb_f32", (double)n * (K + L) * sizeof(float));
+    KTimer kt(ctx, K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny", (double)n * (K + L) * sizeof(float));
     launch_kernel<false, 0>(ctx, p, grid, lay.total);
 }
 
@@ -819,7 +819,7 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.dbg = 0;
     const SmemLayout lay = make_layout(true, n_pad, stages);
     const int grid = (int)(ceil_div(n, p.slice_rows) * fgroups);
-    KTimer kt(ctx, "tc_atb_f32", (double)n * (da + db) * sizeof(float));
+    KTimer kt(ctx, da >= 256 ? "tc_atb_f32" : "tc_atb_f32_skinny", (double)n * (da + db) * sizeof(float));
     switch (n_pad) {
         case 16: launch_kernel<true, 16>(ctx, p, grid, lay.total); break;
         case 32: launch_kernel<true, 32>(ctx, p, grid, lay.total); break;
