@@ -370,6 +370,9 @@ def main():
         except Exception as e:  # host memory too small etc.
             e2e = {"value": None, "unit": "samples/s", "error": str(e)[:200]}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 

@@ -559,11 +559,12 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
              int64_t* n_iter_out, double* lim_out) {
     if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
     symmetric_decorrelation(ctx, w_init, nc, W);  // src/ica.rs:329
-    DBuf<double> Wk(ctx, (size_t)(nc * d)), Hg(ctx, (size_t)(nc * d + nc)), HK(ctx, (size_t)(nc * nc)),
+    DBuf<double> Wk(ctx, (size_t)(nc * d)), Hg(ctx, (size_t)(nc * d)), Htg(ctx, (size_t)(nc * d + nc)), HK(ctx, (size_t)(nc * nc)),
         Gd(ctx, (size_t)(nc * nc)), W1(ctx, (size_t)(nc * nc)), limd(ctx, 1);
     DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, (size_t)(n * nc));
     double* H = Hg.p;
-    double* gp = Hg.p + nc * d;
+    double* Ht = Htg.p;          // [H^T (d x nc) | sum g' (nc)] reduced across ranks together
+    double* gp = Htg.p + nc * d;
     const double inv_n = 1.0 / (double)n_total;
     int64_t iters = max_iter;
     double lim = 0.0;
@@ -580,15 +581,11 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
         // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
         PETAL_CUDA(cudaMemsetAsync(gp, 0, (size_t)nc * sizeof(double), ctx->stream));
         launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp);
-        // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening]
-        PETAL_CUDA(cudaMemsetAsync(H, 0, (size_t)(nc * d) * sizeof(double), ctx->stream));
-        {
-            AtbParams<T> p{};
-            p.A = U.p; p.lda = nc; p.da = nc; p.mua = nullptr; p.B = X; p.ldb = d; p.db = d; p.mub = mu;
-            p.n = n; p.C = H; p.ldc = d; p.symmetric = 0;
-            launch_atb<T>(ctx, p);
-        }
-        allreduce_sum(ctx, Hg.p, (size_t)(nc * d + nc));
+        // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening],
+        // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
+        gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht);
+        allreduce_sum(ctx, Htg.p, (size_t)(nc * d + nc));
+        launch_transpose(ctx, Ht, d, nc, H);
         // Gd = (H K1^T) / n - diag(mean g') W   (src/ica.rs:334-342)
         const double* HKp = H;
         if (K1) {

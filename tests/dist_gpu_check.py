@@ -1,0 +1,79 @@
+"""Multi-GPU parity check, run under torchrun (one process per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_gpu_check.py
+Each rank fits its row shard collectively (NCCL all-reduce inside libpetal_b200); rank 0 compares the
+result with the oracle on the full data."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import petal_decomposition_b200 as pd
+    from petal_decomposition_b200.dist import init_distributed, shard_rows
+    from oracle import ica as oica
+    from oracle import pca as opca
+    from oracle.rng import Mcg128Xsl64
+    from tests import synth
+
+    ctx = init_distributed()
+    rank, world = ctx.rank, ctx.world
+    seed = 1_234_567_891_011_121_314
+    ok = True
+
+    def report(name, cond, detail=""):
+        nonlocal ok
+        if rank == 0:
+            print(f"[dist check] {name}: {'ok' if cond else 'FAIL'} {detail}", flush=True)
+        ok = ok and bool(cond)
+
+    # exact PCA f64
+    x = synth.lowrank_noise(6000, 96, rank=20, decay=0.8, seed=5)
+    r0, r1 = shard_rows(x.shape[0], rank, world)
+    m = pd.Pca.new(6)
+    y = m.fit_transform(np.ascontiguousarray(x[r0:r1]))
+    ref = opca.Pca(6, economy=True)
+    yr = ref.fit_transform(x)
+    err = np.max(np.abs(m.singular_values() - ref.singular_values()) / ref.singular_values())
+    report("pca f64 sigma", err < 1e-10, f"rel err {err:.2e}")
+    report("pca f64 scores (signs incl.)", np.allclose(y, yr[r0:r1], atol=1e-8 * np.abs(yr).max()))
+
+    # randomized PCA f32 (tcgen05 engine)
+    x32 = synth.lowrank_noise(40000, 256, rank=40, decay=0.8, noise=0.01, seed=11, dtype=np.float32)
+    r0, r1 = shard_rows(x32.shape[0], rank, world)
+    omega = Mcg128Xsl64.from_seed_u128(seed).normal_matrix(256, 26, np.float32)
+    rp = pd.RandomizedPcaBuilder.new(16).seed(seed).n_power_iter(4).build()
+    rp.fit(np.ascontiguousarray(x32[r0:r1]))
+    rref = opca.RandomizedPca(16, n_iter=4)
+    rref.fit(x32.astype(np.float64), omega.astype(np.float64))
+    err = np.max(np.abs(rp.singular_values() - rref.singular_values()) / rref.singular_values())
+    report("rpca f32 sigma", err < 1e-4, f"rel err {err:.2e}")
+    ang = opca.principal_angles(rp.components(), rref.components).max()
+    report("rpca f32 subspace", ang < 5e-3, f"max principal angle {ang:.2e}")
+
+    # FastICA f64
+    xi, a = synth.mixed_sources(30000, 6, seed=6)
+    r0, r1 = shard_rows(xi.shape[0], rank, world)
+    ica = pd.FastIca.with_seed(seed)
+    ica.fit(np.ascontiguousarray(xi[r0:r1]))
+    oref = oica.FastIca()
+    oref.fit(xi, Mcg128Xsl64.from_seed_u128(seed).normal_matrix(6, 6))
+    _, defect = oica.match_rows(ica.components, oref.components)
+    report("fastica f64 unmixing rows", defect < 1e-6, f"defect {defect:.2e} n_iter {ica.n_iter}/{oref.n_iter}")
+
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{ctx.device}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("[dist check] ALL OK" if flag.item() == 1 else "[dist check] FAILED", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

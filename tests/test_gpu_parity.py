@@ -451,3 +451,18 @@ def test_tc_atb_engines(pd, n, d, l):
     scale = np.abs(ref).max() + np.sqrt(n)
     assert np.max(np.abs(outs[0] - ref)) < 1e-5 * scale
     assert np.max(np.abs(outs[1] - ref)) < 1e-5 * scale
+
+
+def test_two_gpu_row_sharding(pd):
+    """Row-sharded collective fits on 2 GPUs (NCCL inside the library) against the oracle."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

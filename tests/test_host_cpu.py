@@ -92,3 +92,24 @@ def test_shard_rows():
         spans = [shard_rows(n, r, w) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_cpp_host_mirror_compiles(lib, tmp_path):
+    """include/petal_decomposition.hpp (the C++ host mirror of the reference API) compiles and links
+    against the C ABI; without a GPU it must fail loudly with the reference's error wording."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "host_mirror_test"
+    libdir = os.path.join(ROOT, "petal_decomposition_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                        os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"), "-L", libdir, "-lpetal_b200",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout
+    import torch
+    if torch.cuda.is_available():
+        assert out.split()[:3] == ["5", "0", "5"] or abs(float(out.split()[0]) - 5) < 1e-9
+    else:
+        assert "linear algerba operation failed" in out and "no CPU fallback" in out
