@@ -68,6 +68,8 @@ int64_t petal_ctx_profile_json(petal_ctx* ctx, char* buf, int64_t cap);
 /* Select the f32 streaming-GEMM engine: 0 = FFMA SIMT kernels, 1 = tcgen05 3xTF32 (default when
  * the shape is supported). Returns the engine now in force. Negative `engine` only queries. */
 int petal_ctx_set_f32_engine(petal_ctx* ctx, int engine);
+/* Same for f64 Gram-shaped contractions: 0 = SIMT DFMA kernels, 1 = DMMA (mma.sync.m8n8k4.f64, default). */
+int petal_ctx_set_f64_engine(petal_ctx* ctx, int engine);
 
 /* ---- multi-GPU (row sharding; replaces nothing in the reference, which is single-host) - */
 #define PETAL_COMM_ID_BYTES 128

@@ -35,6 +35,7 @@ SYMBOLS = {
     "petal_ctx_trim": (c_int, [c_vp]),
     "petal_ctx_launch_count": (c_i64, [c_vp]),
     "petal_ctx_set_f32_engine": (c_int, [c_vp, c_int]),
+    "petal_ctx_set_f64_engine": (c_int, [c_vp, c_int]),
     "petal_ctx_set_profiling": (c_int, [c_vp, c_int]),
     "petal_ctx_profile_json": (c_i64, [c_vp, C.c_char_p, c_i64]),
     "petal_comm_unique_id": (c_int, [c_vp]),

@@ -95,6 +95,9 @@ class Context:
         self.lib.petal_ctx_profile_json(self.handle, buf, len(buf))
         return json.loads(buf.value.decode() or "{}")
 
+    def set_f64_engine(self, engine: int) -> int:
+        return int(self.lib.petal_ctx_set_f64_engine(self.handle, int(engine)))
+
     def set_f32_engine(self, engine: int) -> int:
         return int(self.lib.petal_ctx_set_f32_engine(self.handle, int(engine)))
 

@@ -44,6 +44,7 @@ struct petal_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     int f32_engine = 1;  // 0 = SIMT FFMA, 1 = tcgen05 3xTF32 where supported
+    int f64_engine = 1;  // 0 = SIMT DFMA, 1 = DMMA (mma.sync f64) for Gram-shaped contractions
     std::string last_error;
     // optional per-kernel timing (CUDA events on the launch stream), see petal_ctx_profile_json
     bool profiling = false;

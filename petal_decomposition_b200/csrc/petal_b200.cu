@@ -409,44 +409,94 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
 
     // Y = Xc * Omega (src/pca.rs:707), fused with ||Xc||_F^2 (src/pca.rs:533)
     const int64_t ly = ((l + 15) / 16) * 16;  // row pitch of Y: whole 64 B chunks (TMA reads, vector epilogue stores)
-    DBuf<T> Y(ctx, (size_t)(n * ly));
-    DBuf<double> small(ctx, (size_t)(l * l + d * l + 1));  // [G2 | C' | tv] reduced together
+    // f32 on the tcgen05 engine keeps Y panel-major ([row block of 32][ly][32]): tc_xb then writes whole 128 B
+    // lines and tc_atb reads its B tiles by TMA without transposing (see tc_kernels.cuh)
+    bool panel = false;
+    if constexpr (sizeof(T) == 4) {
+        panel = ctx->f32_engine == 1 && tc::xb_supported(X.p, d, n, d, l) && is_aligned16(cm.mu) && n >= 1024 && d >= 32;
+        if (const char* e = getenv("PETAL_PANEL")) panel = panel && atoi(e) != 0;
+    }
+    const int64_t nblk = ceil_div(n, 32);
+    DBuf<T> Y(ctx, panel ? (size_t)(nblk * ly * 32) : (size_t)(n * ly));
+    DBuf<T> Ylo(ctx, panel ? (size_t)(nblk * ly * 32) : 0);  // y - tf32(y), panel-major: B_lo operand of the X^T Y passes
+    DBuf<double> small(ctx, (size_t)(l * l + d * l + 1));  // [Gram of Y | C' | tv] reduced together
     double* G2 = small.p;
     double* Cp = small.p + l * l;
     double* tvd = small.p + l * l + d * l;
+    DBuf<double> P(ctx, (size_t)(l * l));
+    DBuf<T> Y1;
     PETAL_CUDA(cudaMemsetAsync(tvd, 0, sizeof(double), ctx->stream));
-    gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
+    if constexpr (sizeof(T) == 4) {
+        if (panel) tc::launch_tc_xb<float>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, Y.p, ly, tvd, true, Ylo.p);
+    }
+    if (!panel) gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
 
     pc.mark("Y = Xc Omega");
     // power iterations (src/pca.rs:708-715): Z = Xc^T Y, re-orthonormalise, Y = Xc Z
     DBuf<double> Zd(ctx, (size_t)(d * l));
+    auto xty_pass = [&](double* out) {  // out[d x l] = Xc^T Y
+        if constexpr (sizeof(T) == 4) {
+            if (panel) {
+                PETAL_CUDA(cudaMemsetAsync(out, 0, (size_t)(d * l) * sizeof(double), ctx->stream));
+                tc::launch_tc_atb(ctx, X.p, d, d, cm.mu, Y.p, ly, l, n, out, l, true, Ylo.p);
+                return;
+            }
+        }
+        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, ly, l, nullptr, n, out);
+    };
     for (int64_t it = 0; it < n_iter; ++it) {
-        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, ly, l, nullptr, n, Zd.p);
+        xty_pass(Zd.p);
         allreduce_sum(ctx, Zd.p, (size_t)(d * l));
         pc.mark("  Z = Xc^T Y");
         orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
         pc.mark("  orth(Z)");
-        gemm_xb_b64<T>(ctx, X.p, d, n, d, Zd.p, l, l, cm.mu, Y.p, ly);
+        bool done = false;
+        if constexpr (sizeof(T) == 4) {
+            if (panel) {
+                tc::launch_tc_xb<double>(ctx, X.p, d, n, d, Zd.p, l, false, l, cm.mu, Y.p, ly, nullptr, true, Ylo.p);
+                done = true;
+            }
+        }
+        if (!done) gemm_xb_b64<T>(ctx, X.p, d, n, d, Zd.p, l, l, cm.mu, Y.p, ly);
         pc.mark("  Y = Xc Z");
     }
 
-    // thin QR of Y (src/pca.rs:716) done implicitly in two Gram rounds (CholeskyQR2-style, with a
-    // Jacobi eigensolver instead of Cholesky so that rank-deficient Y is handled):
-    //   round 1: Y1 = Y * P1 (materialised),  round 2: Q = Y1 * P2 (implicit)
-    DBuf<double> G1(ctx, (size_t)(l * l)), P(ctx, (size_t)(l * l));
-    DBuf<T> Y1(ctx, (size_t)(n * ly));
-    gemm_atb<T>(ctx, Y.p, ly, l, nullptr, Y.p, ly, l, nullptr, n, G1.p);
-    allreduce_sum(ctx, G1.p, (size_t)(l * l));
-    gram_to_orthonormalizer(ctx, G1.p, l, cutoff, kGramNoise, P.p);
-    pc.mark("G1 = Y^T Y, P1");
-    gemm_xb_b64<T>(ctx, Y.p, ly, n, l, P.p, l, l, nullptr, Y1.p, ly);
-    pc.mark("Y1 = Y P1");
-    // B = Q^T Xc (src/pca.rs:681) = P2^T (Y1^T Xc):  C' = Xc^T Y1 (d x l) in one pass over X
-    gemm_atb<T>(ctx, Y1.p, ly, l, nullptr, Y1.p, ly, l, nullptr, n, G2);
-    gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, ly, l, nullptr, n, Cp);
-    allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
-    pc.mark("G2, C' = Xc^T Y1");
-    gram_to_orthonormalizer(ctx, G2, l, 1e-6, kGramNoise, P.p);  // P2 (l x l)
+    if (panel) {
+        // thin QR of Y (src/pca.rs:716), implicit: G = Y^T Y accumulated in f64 from the exact fp32 products,
+        // P = R^-1 (Cholesky; Jacobi when rank deficient) so that Q = Y P is orthonormal to eps64 * cond(Y)^2.
+        // B = Q^T Xc (src/pca.rs:681) = P^T (Y^T Xc): C' = Xc^T Y in one pass over X.
+        if constexpr (sizeof(T) == 4) {
+            PETAL_CUDA(cudaMemsetAsync(G2, 0, (size_t)(l * l) * sizeof(double), ctx->stream));
+            DBuf<double> Gp(ctx, (size_t)(ly * ly));
+            Gp.zero();
+            launch_panel_gram(ctx, Y.p, n, (int)ly, Gp.p);
+            // compact ly x ly -> l x l
+            PETAL_CUDA(cudaMemcpy2DAsync(G2, (size_t)l * sizeof(double), Gp.p, (size_t)ly * sizeof(double),
+                                         (size_t)l * sizeof(double), (size_t)l, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        xty_pass(Cp);
+        allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
+        pc.mark("G = Y^T Y, C' = Xc^T Y");
+        gram_to_orthonormalizer(ctx, G2, l, cutoff, kGramNoise, P.p);
+    } else {
+        // thin QR of Y (src/pca.rs:716) done implicitly in two Gram rounds (CholeskyQR2-style, with a
+        // Jacobi eigensolver instead of Cholesky when Y is rank deficient):
+        //   round 1: Y1 = Y * P1 (materialised),  round 2: Q = Y1 * P2 (implicit)
+        DBuf<double> G1(ctx, (size_t)(l * l));
+        Y1.alloc(ctx, (size_t)(n * ly));
+        gemm_atb<T>(ctx, Y.p, ly, l, nullptr, Y.p, ly, l, nullptr, n, G1.p);
+        allreduce_sum(ctx, G1.p, (size_t)(l * l));
+        gram_to_orthonormalizer(ctx, G1.p, l, cutoff, kGramNoise, P.p);
+        pc.mark("G1 = Y^T Y, P1");
+        gemm_xb_b64<T>(ctx, Y.p, ly, n, l, P.p, l, l, nullptr, Y1.p, ly);
+        pc.mark("Y1 = Y P1");
+        // B = Q^T Xc (src/pca.rs:681) = P2^T (Y1^T Xc):  C' = Xc^T Y1 (d x l) in one pass over X
+        gemm_atb<T>(ctx, Y1.p, ly, l, nullptr, Y1.p, ly, l, nullptr, n, G2);
+        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, ly, l, nullptr, n, Cp);
+        allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
+        pc.mark("G2, C' = Xc^T Y1");
+        gram_to_orthonormalizer(ctx, G2, l, 1e-6, kGramNoise, P.p);  // P2 (l x l)
+    }
     DBuf<double> M1(ctx, (size_t)(d * l)), Bm(ctx, (size_t)(l * d));
     gemm_xb<double>(ctx, Cp, l, d, l, P.p, l, false, l, nullptr, nullptr, M1.p, l);
     launch_transpose(ctx, M1.p, d, l, Bm.p);  // B (l x d)
@@ -496,7 +546,16 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
             scores_tmp.alloc(ctx, (size_t)(n * k));
             scores_dev = scores_tmp.p;
         }
-        gemm_xb_b64<T>(ctx, Y1.p, ly, n, l, S.p, k, k, nullptr, scores_dev, k);
+        bool done = false;
+        if constexpr (sizeof(T) == 4) {
+            if (panel) {
+                DBuf<float> Sf(ctx, (size_t)(l * k));
+                launch_cast<double, float>(ctx, S.p, Sf.p, l * k);
+                launch_panel_xb(ctx, Y.p, n, (int)ly, (int)l, Sf.p, (int)k, scores_dev, k);
+                done = true;
+            }
+        }
+        if (!done) gemm_xb_b64<T>(ctx, Y1.p, ly, n, l, S.p, k, k, nullptr, scores_dev, k);
         pc.mark("scores = Y1 S");
         flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores);  // svd_flip, src/pca.rs:684
         pc.mark("svd_flip");
@@ -550,6 +609,216 @@ void symmetric_decorrelation(petal_ctx* ctx, const double* W, int64_t m, double*
     gemm_atb<double>(ctx, Jt.p, m, m, nullptr, N.p, m, m, nullptr, m, out);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused small-side update of one FastICA fixed-point iteration (single CTA, f64, nc <= kIcaFusedMax):
+//   Gd = (H K1^T)/n - diag(mean g') W            (reference src/ica.rs:334-342)
+//   W1 = (Gd Gd^T)^-1/2 Gd                        (symmetric_decorrelation, src/ica.rs:363-381) computed as
+//        the polar factor of Gd by the Newton-Schulz iteration X <- X (3I - X^T X)/2, X0 = Gd / sqrt(|Gd|_1 |Gd|_inf)
+//   lim = max_i | |<w1_i, w_i>| - 1 |             (src/ica.rs:344-354; variant 1: rows of w1 with columns of w)
+//   W <- W1,  W~ = W1 K1 (cast to T) for the next streaming pass
+// status[0] = 1 when Newton-Schulz did not converge (singular Gd): the host then redoes the iteration with the
+// Jacobi-based path.
+// ---------------------------------------------------------------------------------------
+constexpr int kIcaFusedMax = 64;
+constexpr int kIcaThreads = 256;
+
+// C = op(A) * B for nc x nc matrices in shared memory (ld = nc + 1).  256 threads as a 16 x 16 grid, each
+// owning the interleaved 4 x 4 outputs (ty + 16u, tx + 16v): B reads are 16 consecutive words per half-warp
+// (conflict-free), A reads are warp broadcasts.  TRANS_A: C = A^T B.  nc <= 64.
+template <bool TRANS_A>
+__device__ __forceinline__ void smem_gemm_k(const double* A, const double* B, double* C, int nc, int kdim, int ld) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4] = {};
+    for (int k = 0; k < kdim; ++k) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = min(ty + 16 * u, nc - 1), j = min(tx + 16 * u, nc - 1);
+            a[u] = TRANS_A ? A[k * ld + i] : A[i * ld + k];
+            b[u] = B[k * ld + j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+            if (ty + 16 * u < nc && tx + 16 * v < nc) C[(ty + 16 * u) * ld + tx + 16 * v] = acc[u][v];
+}
+template <bool TRANS_A>
+__device__ __forceinline__ void smem_gemm(const double* A, const double* B, double* C, int nc, int ld) {
+    smem_gemm_k<TRANS_A>(A, B, C, nc, nc, ld);
+}
+
+__device__ __forceinline__ double block_reduce_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    return s;
+}
+__device__ __forceinline__ double block_reduce_max(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s = fmax(s, red[w]);
+    return s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kIcaThreads)
+ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __restrict__ gp, double* __restrict__ W,
+                  const double* __restrict__ K1 /* nc x d or null */, int nc, int d, double inv_n, int lim_variant,
+                  T* __restrict__ Wt_out /* nc x d */, double* __restrict__ out2 /* [lim, status] */) {
+    extern __shared__ double sm[];
+    const int ld = nc + 1;
+    double* X = sm;
+    double* Tm = sm + (size_t)nc * ld;
+    double* Y = sm + 2 * (size_t)nc * ld;
+    __shared__ double red[kIcaThreads / 32];
+    const int tid = threadIdx.x;
+    const long long c0 = clock64();
+
+    // Gd -> X.  With whitening: HK = H K1^T = (Ht)^T (K1^T): stage Ht (d x nc) in Tm and K1^T (d x nc) in Y
+    // (both need d <= nc-sized buffers: d <= kIcaFusedMax is checked by the host) and multiply in shared memory.
+    if (K1) {
+        for (int e = tid; e < d * nc; e += kIcaThreads) {
+            const int f = e / nc, i = e % nc;
+            Tm[f * ld + i] = Ht[e];                    // Ht[f][i]
+            Y[f * ld + i] = K1[(size_t)i * d + f];     // K1^T[f][i]
+        }
+        __syncthreads();
+        smem_gemm_k<true>(Tm, Y, X, nc, d, ld);        // X = Ht^T K1^T  (nc x nc), reduction over d
+        __syncthreads();
+        for (int e = tid; e < nc * nc; e += kIcaThreads) {
+            const int i = e / nc, j = e % nc;
+            X[i * ld + j] = X[i * ld + j] * inv_n - gp[i] * inv_n * W[e];
+        }
+    } else {
+        for (int e = tid; e < nc * nc; e += kIcaThreads) {
+            const int i = e / nc, j = e % nc;
+            X[i * ld + j] = Ht[(size_t)j * nc + i] * inv_n - gp[i] * inv_n * W[e];
+        }
+    }
+    __syncthreads();
+    const long long c1 = clock64();
+    // scale by sqrt(|Gd|_1 |Gd|_inf) >= |Gd|_2
+    double rs = 0.0, cs = 0.0;
+    for (int i = tid; i < nc; i += kIcaThreads) {
+        double r = 0.0, c = 0.0;
+        for (int j = 0; j < nc; ++j) {
+            r += fabs(X[i * ld + j]);
+            c += fabs(X[j * ld + i]);
+        }
+        rs = fmax(rs, r);
+        cs = fmax(cs, c);
+    }
+    rs = block_reduce_max(rs, red);
+    cs = block_reduce_max(cs, red);
+    const double scale = sqrt(rs * cs);
+    bool ok = (scale > 0.0) && isfinite(scale);
+    if (ok) {
+        const double inv = 1.0 / scale;
+        for (int e = tid; e < nc * nc; e += kIcaThreads) X[(e / nc) * ld + e % nc] *= inv;
+    }
+    __syncthreads();
+    // Newton-Schulz
+    bool converged = false;
+    int ns_it = 0;
+    for (int it = 0; ok && it < 100; ++it) {
+        ns_it = it;
+        smem_gemm<true>(X, X, Tm, nc, ld);  // T = X^T X
+        __syncthreads();
+        double err = 0.0;
+        for (int e = tid; e < nc * nc; e += kIcaThreads) {
+            const int i = e / nc, j = e % nc;
+            const double t = Tm[i * ld + j];
+            const double dlt = t - (i == j ? 1.0 : 0.0);
+            err += dlt * dlt;
+            Tm[i * ld + j] = (i == j ? 1.5 : 0.0) - 0.5 * t;
+        }
+        err = block_reduce_sum(err, red);
+        if (!(err == err)) {
+            ok = false;
+            break;
+        }
+        if (err < 1e-26) {
+            converged = true;
+            break;
+        }
+        smem_gemm<false>(X, Tm, Y, nc, ld);  // Y = X (1.5 I - 0.5 T)
+        __syncthreads();
+        double* t = X;
+        X = Y;
+        Y = t;
+    }
+    if (!converged) {
+        if (tid == 0) {
+            out2[0] = 0.0;
+            out2[1] = 1.0;
+        }
+        return;
+    }
+    const long long c2 = clock64();
+    // lim against the previous W (still in global memory)
+    double best = 0.0;
+    for (int i = tid; i < nc; i += kIcaThreads) {
+        double sdot = 0.0;
+        for (int j = 0; j < nc; ++j) sdot += X[i * ld + j] * (lim_variant ? W[(size_t)j * nc + i] : W[(size_t)i * nc + j]);
+        best = fmax(best, fabs(fabs(sdot) - 1.0));
+    }
+    best = block_reduce_max(best, red);
+    __syncthreads();
+    for (int e = tid; e < nc * nc; e += kIcaThreads) W[e] = X[(e / nc) * ld + e % nc];
+    // W~ = W1 K1 for the next pass
+    if (K1) {
+        __syncthreads();
+        for (int e = tid; e < nc * d; e += kIcaThreads) Tm[(e / d) * ld + e % d] = K1[e];  // K1 (nc x d)
+        __syncthreads();
+        // Y (nc x d) = X (nc x nc) * K1 (nc x d): output columns d <= 64 handled by the same 16 x 16 grid
+        {
+            const int ty = tid >> 4, tx = tid & 15;
+            double acc[4][4] = {};
+            for (int k = 0; k < nc; ++k) {
+                double a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    a[u] = X[min(ty + 16 * u, nc - 1) * ld + k];
+                    b[u] = Tm[k * ld + min(tx + 16 * u, d - 1)];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) acc[u][v] += a[u] * b[v];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (ty + 16 * u < nc && tx + 16 * v < d) Wt_out[(size_t)(ty + 16 * u) * d + tx + 16 * v] = (T)acc[u][v];
+        }
+    } else {
+        for (int e = tid; e < nc * d; e += kIcaThreads) Wt_out[e] = (T)X[(e / d) * ld + e % d];
+    }
+    if (tid == 0) {
+        out2[0] = best;
+        out2[1] = 0.0;
+        out2[2] = (double)ns_it;
+        out2[3] = (double)(c1 - c0);
+        out2[4] = (double)(c2 - c1);
+        out2[5] = (double)(clock64() - c2);
+    }
+}
+
 // ica_par (reference src/ica.rs:319-361) on data X[n x d] with whitening folded in:
 // the whitened sample is x1 = K1 (x - mu) with K1 = sqrt(n) K (nc x d); K1 == nullptr means the
 // data is already white (d == nc).  Returns W (nc x nc, f64, device) and the iteration count.
@@ -568,7 +837,17 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
     const double inv_n = 1.0 / (double)n_total;
     int64_t iters = max_iter;
     double lim = 0.0;
-    for (int64_t it = 0; it < max_iter; ++it) {
+    const bool fused = (nc <= kIcaFusedMax) && (d <= kIcaFusedMax);
+    DBuf<double> out2(ctx, 8);
+    if (fused) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            PETAL_CUDA(cudaFuncSetAttribute(ica_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            3 * kIcaFusedMax * (kIcaFusedMax + 1) * (int)sizeof(double)));
+            attr_set = true;
+        }
+    }
+    auto make_wt = [&]() {
         // W~ = W K1 so that W x1 = W~ (x - mu): the whitened copy is never materialised
         const double* Wfull = W;
         if (K1) {
@@ -576,6 +855,9 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
             Wfull = Wk.p;
         }
         launch_cast<double, T>(ctx, Wfull, Wt.p, nc * d);
+    };
+    make_wt();
+    for (int64_t it = 0; it < max_iter; ++it) {
         // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
         gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
         // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
@@ -585,21 +867,39 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
         // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
         gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht);
         allreduce_sum(ctx, Htg.p, (size_t)(nc * d + nc));
-        launch_transpose(ctx, Ht, d, nc, H);
-        // Gd = (H K1^T) / n - diag(mean g') W   (src/ica.rs:334-342)
-        const double* HKp = H;
-        if (K1) {
-            gemm_xb<double>(ctx, H, d, nc, d, K1, d, true, nc, nullptr, nullptr, HK.p, nc);
-            HKp = HK.p;
+        bool done_small = false;
+        if (fused) {
+            KTimer kt(ctx, "ica_update", 0.0);
+            ica_update_kernel<T><<<1, kIcaThreads, 3 * (size_t)nc * (nc + 1) * sizeof(double), ctx->stream>>>(
+                Ht, gp, W, K1, (int)nc, (int)d, inv_n, lim_variant, Wt.p, out2.p);
+            launch1(ctx);
+            double h2[8] = {0.0, 1.0};
+            PETAL_CUDA(cudaMemcpyAsync(h2, out2.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (getenv("PETAL_PHASES")) fprintf(stderr, "[ica_update] it %lld lim %.3e ns_iters %.0f cycles: setup %.0f ns %.0f tail %.0f\n", (long long)it, h2[0], h2[2], h2[3], h2[4], h2[5]);
+            if (h2[1] == 0.0) {
+                lim = h2[0];
+                done_small = true;
+            }
         }
-        ica_gd_kernel<<<(unsigned)ceil_div(nc * nc, 256), 256, 0, ctx->stream>>>(HKp, gp, W, nc, inv_n, Gd.p);
-        launch1(ctx);
-        symmetric_decorrelation(ctx, Gd.p, nc, W1.p);  // src/ica.rs:343
-        ica_lim_kernel<<<1, 256, 0, ctx->stream>>>(W1.p, W, (int)nc, lim_variant, limd.p);
-        launch1(ctx);
-        PETAL_CUDA(cudaMemcpyAsync(W, W1.p, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        PETAL_CUDA(cudaMemcpyAsync(&lim, limd.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!done_small) {
+            launch_transpose(ctx, Ht, d, nc, H);
+            // Gd = (H K1^T) / n - diag(mean g') W   (src/ica.rs:334-342)
+            const double* HKp = H;
+            if (K1) {
+                gemm_xb<double>(ctx, H, d, nc, d, K1, d, true, nc, nullptr, nullptr, HK.p, nc);
+                HKp = HK.p;
+            }
+            ica_gd_kernel<<<(unsigned)ceil_div(nc * nc, 256), 256, 0, ctx->stream>>>(HKp, gp, W, nc, inv_n, Gd.p);
+            launch1(ctx);
+            symmetric_decorrelation(ctx, Gd.p, nc, W1.p);  // src/ica.rs:343
+            ica_lim_kernel<<<1, 256, 0, ctx->stream>>>(W1.p, W, (int)nc, lim_variant, limd.p);
+            launch1(ctx);
+            PETAL_CUDA(cudaMemcpyAsync(W, W1.p, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            PETAL_CUDA(cudaMemcpyAsync(&lim, limd.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            make_wt();
+        }
         if (lim < tol) {  // src/ica.rs:355-357
             iters = it + 1;
             break;
@@ -747,6 +1047,12 @@ int petal_ctx_set_f32_engine(petal_ctx* ctx, int engine) {
     if (!ctx) return -1;
     if (engine >= 0) ctx->f32_engine = engine ? 1 : 0;
     return ctx->f32_engine;
+}
+
+int petal_ctx_set_f64_engine(petal_ctx* ctx, int engine) {
+    if (!ctx) return -1;
+    if (engine >= 0) ctx->f64_engine = engine ? 1 : 0;
+    return ctx->f64_engine;
 }
 
 int petal_ctx_set_profiling(petal_ctx* ctx, int enable) {

@@ -486,6 +486,143 @@ void launch_atb_t(petal_ctx* ctx, AtbParams<T> p, bool aligned) {
     check_launch(ctx);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// atb on the FP64 tensor path (DMMA, mma.sync.m8n8k4.f64): C[da x db] (f64) += (A - mua)^T (B - mub)
+// 128 x 128 output tile per CTA over a slice of rows; 8 warps as 4 (i) x 2 (j), each 32 x 64 = 4 x 8 DMMA tiles.
+// Shared tiles keep the natural [row][feature] layout with a 64 B row skew so that the four K rows a fragment
+// load touches fall into both halves of the bank space (2 wavefronts = the minimum for 256 B).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256) atb_dmma_kernel(AtbParams<double> p) {
+    constexpr int BI = 128, BJ = 128, BR = 16, LDS_ = BI + 8;
+    constexpr int A_VECS = BR * BI / 2 / 256;  // 4 double2 per thread per operand
+    __shared__ __align__(16) double As[BR * LDS_];
+    __shared__ __align__(16) double Bs[BR * LDS_];
+
+    const int tile_i = blockIdx.x / p.tiles_j, tile_j = blockIdx.x % p.tiles_j;
+    if (p.symmetric && tile_j < tile_i) return;
+    const int64_t i0 = (int64_t)tile_i * BI, j0 = (int64_t)tile_j * BJ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = warp >> 1, wj = warp & 1;
+    const int64_t r_begin = (int64_t)blockIdx.y * p.rows_per_cta;
+    const int64_t r_end = min(p.n, r_begin + p.rows_per_cta);
+    if (r_begin >= r_end) return;
+    const bool same = p.symmetric && (tile_i == tile_j);  // diagonal tile: B tile == A tile
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    Pack<double> a_stage[A_VECS], b_stage[A_VECS];
+    auto load_one = [&](const double* M, int64_t ld, int64_t ncol, const double* mu, int64_t c0, int64_t r0,
+                        Pack<double>* stage) {
+#pragma unroll
+        for (int q = 0; q < A_VECS; ++q) {
+            int idx = tid + q * 256;
+            int rr = idx / (BI / 2), cv = idx % (BI / 2);
+            int64_t r = r0 + rr, c = c0 + cv * 2;
+            Pack<double> z;
+            z.v[0] = z.v[1] = 0.0;
+            if (r < r_end && c < ncol) {
+                if constexpr (ALIGNED) {
+                    z = *reinterpret_cast<const Pack<double>*>(M + r * ld + c);
+                    if (mu) {
+                        z.v[0] -= mu[c];
+                        z.v[1] -= mu[c + 1];
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v)
+                        if (c + v < ncol) z.v[v] = M[r * ld + c + v] - (mu ? mu[c + v] : 0.0);
+                }
+            }
+            stage[q] = z;
+        }
+    };
+    auto load_tiles = [&](int64_t r0) {
+        load_one(p.A, p.lda, p.da, p.mua, i0, r0, a_stage);
+        if (!same) load_one(p.B, p.ldb, p.db, p.mub, j0, r0, b_stage);
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int q = 0; q < A_VECS; ++q) {
+            int idx = tid + q * 256;
+            int rr = idx / (BI / 2), cv = idx % (BI / 2);
+            *reinterpret_cast<Pack<double>*>(&As[rr * LDS_ + cv * 2]) = a_stage[q];
+            if (!same) *reinterpret_cast<Pack<double>*>(&Bs[rr * LDS_ + cv * 2]) = b_stage[q];
+        }
+    };
+
+    load_tiles(r_begin);
+    store_tiles();
+    __syncthreads();
+    const double* Bt = same ? As : Bs;
+    const int kq = lane & 3, rq = lane >> 2;
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += BR) {
+        const bool has_next = (r0 + BR) < r_end;
+        if (has_next) load_tiles(r0 + BR);
+#pragma unroll
+        for (int k4 = 0; k4 < BR / 4; ++k4) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[(k4 * 4 + kq) * LDS_ + wi * 32 + a * 8 + rq];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) bf[b] = Bt[(k4 * 4 + kq) * LDS_ + wj * 64 + b * 8 + rq];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();
+        if (has_next) {
+            store_tiles();
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int64_t gi = i0 + wi * 32 + a * 8 + rq;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int64_t gj = j0 + wj * 64 + b * 8 + 2 * kq;
+            if (gi < p.da) {
+                if (gj < p.db) atomicAdd(&p.C[gi * p.ldc + gj], acc[a][b][0]);
+                if (gj + 1 < p.db) atomicAdd(&p.C[gi * p.ldc + gj + 1], acc[a][b][1]);
+            }
+        }
+    }
+}
+
+inline void launch_atb_dmma(petal_ctx* ctx, AtbParams<double> p, bool aligned) {
+    int64_t tiles_i = ceil_div(p.da, 128), tiles_j = ceil_div(p.db, 128);
+    p.tiles_j = (int)tiles_j;
+    int64_t tiles = tiles_i * tiles_j;
+    int64_t eff_tiles = p.symmetric ? (tiles_i * (tiles_i + 1)) / 2 : tiles;
+    int64_t target = (int64_t)ctx->sm_count * 2;
+    int64_t gy = std::max<int64_t>(1, target / std::max<int64_t>(1, eff_tiles));
+    gy = std::min<int64_t>(gy, ceil_div(p.n, 256));
+    gy = std::min<int64_t>(std::max<int64_t>(gy, 1), 65535);
+    int64_t rows = ceil_div(ceil_div(p.n, gy), 16) * 16;
+    p.rows_per_cta = rows;
+    gy = ceil_div(p.n, rows);
+    dim3 grid((unsigned)tiles, (unsigned)gy);
+    KTimer kt(ctx, "atb_dmma_f64", (double)p.n * ((p.symmetric ? 0 : p.da) + p.db) * sizeof(double));
+    if (aligned)
+        atb_dmma_kernel<true><<<grid, 256, 0, ctx->stream>>>(p);
+    else
+        atb_dmma_kernel<false><<<grid, 256, 0, ctx->stream>>>(p);
+    check_launch(ctx);
+}
+
 // C must be zeroed by the caller (the kernel accumulates).
 template <typename T>
 void launch_atb(petal_ctx* ctx, AtbParams<T> p) {
@@ -493,6 +630,14 @@ void launch_atb(petal_ctx* ctx, AtbParams<T> p) {
     constexpr int V = Pack<T>::N;
     bool aligned = (p.da % V == 0) && (p.lda % V == 0) && is_aligned16(p.A) &&
                    (p.mua == nullptr || is_aligned16(p.mua));
+    if constexpr (sizeof(T) == 8) {
+        // FP64 tensor path for Gram-shaped work (both output dimensions fill a good part of a 128 x 128 tile)
+        if (ctx->f64_engine == 1 && p.da >= 96 && p.db >= 96 && p.n >= 64) {
+            bool al2 = aligned && (p.db % V == 0) && (p.ldb % V == 0) && is_aligned16(p.B);
+            launch_atb_dmma(ctx, p, al2);
+            return;
+        }
+    }
     if (p.symmetric) {
         launch_atb_t<T, 8, 8>(ctx, p, aligned);
         return;
@@ -504,6 +649,168 @@ void launch_atb(petal_ctx* ctx, AtbParams<T> p) {
     else if (p.db <= 80) launch_atb_t<T, 8, 5>(ctx, p, aligned);
     else if (p.db <= 96) launch_atb_t<T, 8, 6>(ctx, p, aligned);
     else launch_atb_t<T, 8, 8>(ctx, p, aligned);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Panel-major Y ([row block of 32][np][32] floats, np = columns rounded up to 16; see tc_kernels.cuh):
+//   panel_gram : G[np x np] (f64) += Y^T Y
+//   panel_xb   : out[n x k] (row-major) = Y * S,  S[l x k] row-major
+// Skinny, Y-sized passes of the randomized-PCA epilogue (G1 = Y^T Y, scores = Q U_B Sigma).
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256)
+panel_gram_kernel(const float* __restrict__ Yp, int64_t nblocks, int64_t blocks_per_cta, double* __restrict__ G) {
+    constexpr int TI = NP / 16;  // outputs per thread per dimension (16 x 16 thread grid, interleaved)
+    __shared__ float Ts[32][NP + 1];  // [row in block][column]
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int64_t b0 = (int64_t)blockIdx.x * blocks_per_cta;
+    const int64_t b1 = min(nblocks, b0 + blocks_per_cta);
+    float acc[TI][TI];
+    double dacc[TI][TI];
+#pragma unroll
+    for (int u = 0; u < TI; ++u)
+#pragma unroll
+        for (int v = 0; v < TI; ++v) {
+            acc[u][v] = 0.f;
+            dacc[u][v] = 0.0;
+        }
+    int since = 0;
+    auto flush = [&]() {  // fp32 partial sums (<= 2048 rows) -> f64 registers
+#pragma unroll
+        for (int u = 0; u < TI; ++u)
+#pragma unroll
+            for (int v = 0; v < TI; ++v) {
+                dacc[u][v] += (double)acc[u][v];
+                acc[u][v] = 0.f;
+            }
+    };
+    for (int64_t b = b0; b < b1; ++b) {
+        const float* src = Yp + b * NP * 32;
+        __syncthreads();
+        for (int e = tid; e < NP * 32; e += 256) Ts[e & 31][e >> 5] = src[e];  // coalesced read, transposed store
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+            float a[TI], bb[TI];
+#pragma unroll
+            for (int u = 0; u < TI; ++u) {
+                a[u] = Ts[i][ty + 16 * u];
+                bb[u] = Ts[i][tx + 16 * u];
+            }
+#pragma unroll
+            for (int u = 0; u < TI; ++u)
+#pragma unroll
+                for (int v = 0; v < TI; ++v) acc[u][v] += a[u] * bb[v];
+        }
+        if (++since == 64) {
+            flush();
+            since = 0;
+        }
+    }
+    flush();
+#pragma unroll
+    for (int u = 0; u < TI; ++u)
+#pragma unroll
+        for (int v = 0; v < TI; ++v) atomicAdd(&G[(ty + 16 * u) * NP + tx + 16 * v], dacc[u][v]);
+}
+
+// G must be zeroed by the caller; np in {16, 32, ..., 128}
+inline void launch_panel_gram(petal_ctx* ctx, const float* Yp, int64_t n, int np, double* G) {
+    const int64_t nblocks = ceil_div(n, 32);
+    int64_t ctas = std::min<int64_t>(nblocks, (int64_t)ctx->sm_count * 4);
+    const int64_t per = ceil_div(nblocks, ctas);
+    ctas = ceil_div(nblocks, per);
+    KTimer kt(ctx, "panel_gram_f32", (double)n * np * sizeof(float));
+    switch (np) {
+        case 16: panel_gram_kernel<16><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        case 32: panel_gram_kernel<32><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        case 48: panel_gram_kernel<48><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        case 64: panel_gram_kernel<64><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        case 80: panel_gram_kernel<80><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        case 96: panel_gram_kernel<96><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        case 112: panel_gram_kernel<112><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+        default: panel_gram_kernel<128><<<(unsigned)ctas, 256, 0, ctx->stream>>>(Yp, nblocks, per, G); break;
+    }
+    check_launch(ctx);
+}
+
+// out[r][j] = sum_c Y[r][c] * S[c][j]; CTAs loop over pairs of row blocks (64 rows); S staged once in shared
+// memory (l x kp floats, kp = k rounded up to 32*KV).  256 threads = 8 (row groups) x 32 (column groups): each thread
+// owns rows i0 + 8u (u < 8) and the KV contiguous columns KV*j0 ... (one vector load of S per c).
+template <int KV>
+__global__ void __launch_bounds__(256)
+panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const float* __restrict__ S, int k,
+                float* __restrict__ out, int64_t ldo) {
+    extern __shared__ float psm[];
+    constexpr int KP = 32 * KV;
+    float* Ss = psm;                   // [l][KP]
+    float* Ts = psm + (size_t)l * KP;  // [np][65]: column c of the 64 rows at c*65 + i
+    const int tid = threadIdx.x;
+    for (int e = tid; e < l * KP; e += 256) {
+        const int c = e / KP, j = e % KP;
+        Ss[e] = (j < k) ? S[c * k + j] : 0.f;
+    }
+    const int64_t nblocks = (n + 31) / 32;
+    const int64_t npairs = (nblocks + 1) / 2;
+    const int i0 = tid >> 5, j0 = tid & 31;
+    for (int64_t pb = blockIdx.x; pb < npairs; pb += gridDim.x) {
+        __syncthreads();
+        for (int h = 0; h < 2; ++h) {
+            const int64_t b = pb * 2 + h;
+            if (b < nblocks) {
+                const float* src = Yp + b * np * 32;
+                for (int e = tid; e < np * 32; e += 256) Ts[(e >> 5) * 65 + h * 32 + (e & 31)] = src[e];
+            }
+        }
+        __syncthreads();
+        float acc[8][KV];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int v = 0; v < KV; ++v) acc[u][v] = 0.f;
+        for (int c = 0; c < l; ++c) {
+            float y[8], sv[KV];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y[u] = Ts[c * 65 + i0 + 8 * u];  // warp broadcast
+#pragma unroll
+            for (int v = 0; v < KV; ++v) sv[v] = Ss[c * KP + KV * j0 + v];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < KV; ++v) acc[u][v] += y[u] * sv[v];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t r = pb * 64 + i0 + 8 * u;
+            if (r < n) {
+#pragma unroll
+                for (int v = 0; v < KV; ++v)
+                    if (KV * j0 + v < k) out[r * ldo + KV * j0 + v] = acc[u][v];
+            }
+        }
+    }
+}
+
+inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, int l, const float* S, int k,
+                            float* out, int64_t ldo) {
+    if (n == 0 || k == 0) return;
+    const int kv = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
+    size_t smem = ((size_t)l * 32 * kv + 65 * (size_t)np) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr = true;
+    }
+    const int64_t nblocks = ceil_div(n, 32);
+    const int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->sm_count * 4);
+    KTimer kt(ctx, "panel_xb_f32", (double)n * (np + k) * sizeof(float));
+    if (k <= 32) panel_xb_kernel<1><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo);
+    else if (k <= 64) panel_xb_kernel<2><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo);
+    else panel_xb_kernel<4><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo);
+    check_launch(ctx);
 }
 
 __global__ void symmetrize_kernel(double* C, int64_t d, int64_t ldc) {

@@ -174,7 +174,7 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int n, int b_mn_major) {
 // ------------------------------------------------------------------------------------------
 struct TcParams {
     CUtensorMap map_x;    // tc_xb : X as {K inner, rows}, box {32, 256}, SWIZZLE_128B
-                          // tc_atb: X as {features inner, rows}, box {256, 32}, no swizzle
+                          // tc_atb: X as {features inner, rows}, 8 boxes {32, 32}, SWIZZLE_128B
     CUtensorMap map_bhi;  // tc_xb : B^T hi as {K inner, n_pad}, box {32, n_pad}, SWIZZLE_128B
                           // tc_atb: Y as {cols inner, rows}, box {n_pad, 32}, no swizzle
     CUtensorMap map_blo;  // tc_xb : B^T lo (same shape as hi); unused by tc_atb
@@ -183,11 +183,14 @@ struct TcParams {
     int64_t K;            // tc_xb: reduction length (features); tc_atb: da (features)
     int n_pad;            // MMA N (multiple of 16, <= 128)
     int L;                // valid output columns
-    int stages;
+    int stages;           // X ring depth (X tile + mu slice; released as soon as the transform has read it)
+    int stages_b;         // B ring depth (B / Y tiles; released by the MMAs, or by the transform for row-major Y)
     // tc_xb outputs
     float* Y;
+    float* Ylo;           // tc_xb panel mode: second panel with y - tf32(y) (the B_lo operand of a later tc_atb)
     int64_t ldy;
     int y_vec;            // Y rows may be written with 16 B stores
+    int y_panel;          // tc_xb: write Y panel-major [row block of 32][n_pad][32]; tc_atb: B operand is panel-major
     double* sumsq;        // nullable
     // tc_atb outputs / decomposition
     double* Z;            // [da x ldz] f64, atomically accumulated
@@ -205,19 +208,21 @@ struct SmemLayout {
 };
 
 // One carve-up shared by host (size) and device (offsets). Offsets are relative to a 1024 B aligned base.
-__host__ __device__ inline SmemLayout make_layout(bool atb, int n_pad, int stages) {
+__host__ __device__ inline SmemLayout make_layout(bool atb, int n_pad, int stages, int stages_b, bool panel = false) {
     SmemLayout l;
     l.stage_x = kXStageBytes;
-    l.stage_b = (uint32_t)n_pad * 128u;   // tc_xb: B^T tile [n_pad][32]; tc_atb: raw Y tile [32][n_pad]
+    l.stage_b = (uint32_t)n_pad * 128u;   // tc_xb: B^T tile [n_pad][32]; tc_atb: Y tile (raw [32][n_pad] or panel [n_pad][32])
     l.stage_mu = 128;
-    l.ylo_bytes = atb ? 2u * (uint32_t)n_pad * 128u : 0u;  // tc_atb: K-major Y_hi | Y_lo tiles [n_pad][32], ring of kYBufs
+    // tc_atb, row-major Y: ring of kYBufs K-major operand tiles [n_pad][32], Y_hi | Y_lo, produced by the transform
+    // warps (transpose + split).  Panel-major Y needs none of that: Y_hi / Y_lo panels are TMA-loaded like tc_xb's B.
+    l.ylo_bytes = (atb && !panel) ? 2u * (uint32_t)n_pad * 128u : 0u;
     uint32_t off = 0;
     l.x = off;
     off += (uint32_t)stages * l.stage_x;
     l.bhi = off;
-    off += (uint32_t)stages * l.stage_b;
+    off += (uint32_t)stages_b * l.stage_b;
     l.blo = off;
-    off += atb ? 0u : (uint32_t)stages * l.stage_b;
+    off += (atb && !panel) ? 0u : (uint32_t)stages_b * l.stage_b;
     l.ylo = off;
     off += (uint32_t)kYBufs * l.ylo_bytes;
     l.mu = off;
@@ -230,21 +235,25 @@ __host__ __device__ inline SmemLayout make_layout(bool atb, int n_pad, int stage
     return l;
 }
 
-inline int pick_stages(bool atb, int n_pad) {
-    for (int s = 6; s >= 2; --s)
-        if (make_layout(atb, n_pad, s).total <= 220 * 1024) return s;
-    return 0;
+// The X ring is what hides HBM latency (a stage is recycled as soon as the transform warps have pulled it into
+// registers); the B ring only has to cover the MMA latency.  Give B three stages and X the rest.
+inline bool pick_stages(bool atb, int n_pad, bool panel, int& sx, int& sb) {
+    for (sb = 3; sb >= 2; --sb)
+        for (sx = 7; sx >= 2; --sx)
+            if (make_layout(atb, n_pad, sx, sb, panel).total <= 222 * 1024) return true;
+    return false;
 }
 
-// barrier indices inside the `bars` block
-__device__ __forceinline__ uint32_t bar_full(uint32_t base, int s) { return base + 8u * (uint32_t)s; }
+// barrier indices inside the `bars` block (64 slots)
+__device__ __forceinline__ uint32_t bar_full(uint32_t base, int s) { return base + 8u * (uint32_t)s; }            // X ring
 __device__ __forceinline__ uint32_t bar_empty_x(uint32_t base, int s) { return base + 8u * (8 + (uint32_t)s); }
-__device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (16 + (uint32_t)s); }
-__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (24 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (26 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 28; }
-__device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 29; }
+__device__ __forceinline__ uint32_t bar_full_b(uint32_t base, int s) { return base + 8u * (16 + (uint32_t)s); }   // B ring
+__device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (24 + (uint32_t)s); }
+__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (34 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 36; }
+__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 37; }
+__device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (40 + (uint32_t)t); }
 
 // ------------------------------------------------------------------------------------------
 // the kernel (ATB = false: tc_xb, ATB = true: tc_atb; NP = compile-time n_pad for tc_atb)
@@ -259,7 +268,7 @@ __device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base +
 //           (round-to-nearest) and only the CTA's final sums go to global memory (f64 atomics).
 // ------------------------------------------------------------------------------------------
 constexpr int kTraceKB = 512;   // K blocks traced (CTA 0 only)
-constexpr int kTraceEvents = 8;
+constexpr int kTraceEvents = 12;
 __device__ __forceinline__ void trace_ev(const TcParams& p, int ev, uint32_t it) {
     if (p.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceKB) p.trace[ev * kTraceKB + it] = clock64();
 }
@@ -313,6 +322,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
         const int lrow = q * 32 + lane;           // lane (= row / feature) inside the M tile
         const uint32_t lane_field = (uint32_t)(q * 32) << 16;
         const int ttid = threadIdx.x;             // 0 .. 511
+        const bool panel = p.y_panel != 0;
         uint32_t it = 0;
         double ss = 0.0;
         float racc[(ATB && EPI) ? NP : 1];
@@ -348,11 +358,19 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 uint32_t v[16];
                 const uint8_t* xs = base_ptr + L.x + (uint32_t)s * L.stage_x;
                 if (ATB) {
-                    // tile [32 rows][256 features] row-major: this thread owns one feature (transpose)
-                    // and the K rows 16*half .. 16*half+15
-                    const float* xf = reinterpret_cast<const float*>(xs) + (half * 16) * 256 + mt * 128 + lrow;
+                    // 8 sub-tiles [32 rows][32 features] (128 B rows, SWIZZLE_128B): this thread owns one feature
+                    // (transpose) and the K rows 16*half .. 16*half+15
+                    const int f = mt * 128 + lrow;
+                    const uint8_t* xsub = xs + (f >> 5) * 4096 + (f & 3) * 4;
+                    const int fc = (f & 31) >> 2;  // 16 B chunk of the feature inside its 128 B row
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(xf[k * 256] - mu_f);
+                    for (int k = 0; k < 16; ++k) {
+                        const int kr = half * 16 + k;
+                        v[k] = __float_as_uint(*reinterpret_cast<const float*>(xsub + kr * 128 + ((fc ^ (kr & 7)) << 4)) - mu_f);
+                    }
+                    __syncwarp();  // smem X stage consumed (values are in registers)
+                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
+                    if (warp == 0 && lane == 0) trace_ev(p, 7, it);
                 } else {
                     // tile [256 rows][32 floats], 128 B rows, SWIZZLE_128B: this thread owns one row and
                     // the 16 B chunks 4*half .. 4*half+3 of it
@@ -379,12 +397,17 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                     __syncwarp();  // smem X stage consumed (values are in registers)
                     if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
                 }
-                if (ATB) {
-                    // B operand of this K block: raw Y tile [32 rows][n_pad] (row-major) -> transposed
-                    // K-major tiles Y_hi / Y_lo [n_pad][32 rows] with the 128 B swizzle the MMA expects.
-                    const float* yr = reinterpret_cast<const float*>(base_ptr + L.bhi + (uint32_t)s * L.stage_b);
+                if (ATB && !panel) {
+                    const int sb = (int)(it % (uint32_t)p.stages_b);
+                    mbar_wait(bar_full_b(bars, sb), (it / (uint32_t)p.stages_b) & 1u);  // Y tile landed
+                    if (warp == 0 && lane == 0) trace_ev(p, 8, it);
                     const int yb = (int)(it % (uint32_t)kYBufs);
                     mbar_wait(bar_y_free(bars, yb), ((it / (uint32_t)kYBufs) & 1u) ^ 1u);  // MMAs of K block it-3 done
+                    if (warp == 0 && lane == 0) trace_ev(p, 9, it);
+                    {
+                    // B operand of this K block: raw Y tile [32 rows][n_pad] (row-major) -> transposed
+                    // K-major tiles Y_hi / Y_lo [n_pad][32 rows] with the 128 B swizzle the MMA expects.
+                    const float* yr = reinterpret_cast<const float*>(base_ptr + L.bhi + (uint32_t)sb * L.stage_b);
                     uint8_t* bh = base_ptr + L.ylo + (uint32_t)yb * L.ylo_bytes;
                     uint8_t* bl = bh + n_pad * 128;
 #pragma unroll
@@ -403,9 +426,10 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                         *reinterpret_cast<float4*>(bh + y_dst[u]) = h;
                         *reinterpret_cast<float4*>(bl + y_dst[u]) = l4;
                     }
+                    }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_empty_x(bars, s));  // X and raw Y stage consumed
+                    if (lane == 0) mbar_arrive(bar_empty_b(bars, sb));  // TMA-landed Y tile consumed
                 }
                 // TMEM operand stage `ta` must have been drained by the MMAs of two K blocks ago
                 if (warp == 0 && lane == 0) trace_ev(p, 4, it);
@@ -443,6 +467,29 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                         for (int j = 0; j < 16; ++j) racc[c0 + j] += __uint_as_float(w[j]);
                     }
                 } else if constexpr (!ATB) {
+                    if (panel) {
+                        // panel-major Y [row block of 32][n_pad][32]: lane = row inside the block, so for each
+                        // column the warp writes one full 128 B line.  The two warps of a lane-quarter pair
+                        // take alternate 16-column chunks.  Rows past n are written as zeros.
+                        const int64_t r = g.row0 + mt * 128 + lrow;
+                        const int64_t rblk = (g.row0 + mt * 128 + q * 32) >> 5;
+                        float* yb = p.Y + (rblk * n_pad) * 32 + lane;
+                        float* yl = p.Ylo + (rblk * n_pad) * 32 + lane;
+                        const bool valid = r < p.n;
+                        const bool blk_valid = rblk * 32 < p.n;  // the panel buffer ends at the last partial row block
+                        for (int c0 = half * 16; c0 < n_pad; c0 += 32) {
+                            uint32_t w[16];
+                            tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad + c0), w);
+                            tmem_ld_wait();
+                            if (!blk_valid) continue;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float y = valid ? __uint_as_float(w[j]) : 0.f;
+                                yb[(c0 + j) * 32] = y;
+                                yl[(c0 + j) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
+                            }
+                        }
+                    } else {
                     // Each warp of a lane-quarter pair drains 16 of the 32 lanes with the 16x256b pattern:
                     // four lanes hold 8 consecutive columns of one row, so every store instruction writes
                     // whole 32 B sectors (8 rows x 32 B).
@@ -482,6 +529,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                             }
                         }
                     }
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -512,16 +560,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int n_pad = ATB ? NP : p.n_pad;
-    const SmemLayout L = make_layout(ATB, n_pad, p.stages);
+    const bool panel = p.y_panel != 0;
+    const SmemLayout L = make_layout(ATB, n_pad, p.stages, p.stages_b, ATB && panel);
     const uint32_t bars = base + L.bars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int S = p.stages;
+    const int S = p.stages, SB = p.stages_b;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(bar_full(bars, s), 1);
             mbar_init(bar_empty_x(bars, s), kTransformWarps);
-            mbar_init(bar_empty_b(bars, s), kMT);
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(bar_full_b(bars, s), 1);
+            // released by the two MMA warps, or by the transform warps when they consume the raw row-major Y tile
+            mbar_init(bar_empty_b(bars, s), (ATB && !panel) ? kTransformWarps : kMT);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(bar_a_ready(bars, t), kTransformWarps);
@@ -537,12 +590,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L.tmem_slot);
-    const uint32_t stage_tx = ATB ? (L.stage_x + L.stage_b) : (L.stage_x + 2u * L.stage_b + L.stage_mu);
 
     if (warp >= kTransformWarps) {
         if (ATB) reg_dealloc<40>();
         if (warp == kTransformWarps) {
-            // ================================ TMA producer ================================
+            // ================================ TMA producer: X ring ================================
             if (lane == 0) {
                 uint32_t it = 0;
                 Group g;
@@ -551,20 +603,52 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         const int s = (int)(it % (uint32_t)S);
                         const uint32_t ph = (it / (uint32_t)S) & 1u;
                         mbar_wait(bar_empty_x(bars, s), ph ^ 1u);
-                        if (!ATB) mbar_wait(bar_empty_b(bars, s), ph ^ 1u);
                         trace_ev(p, 0, it);
                         const uint32_t full = bar_full(bars, s);
-                        mbar_expect_tx(full, stage_tx);
                         if (ATB) {
-                            const int r = (int)(g.row0 + kb * kKB);
-                            tma_load_2d(base + L.x + (uint32_t)s * L.stage_x, &p.map_x, g.f0, r, full);
-                            tma_load_2d(base + L.bhi + (uint32_t)s * L.stage_b, &p.map_bhi, 0, r, full);
+                            // 8 sub-tiles of 32 features x 32 rows (128 B rows, SWIZZLE_128B): the wide un-swizzled box
+                            // {256 features, 32 rows} was served at only ~15 B/clk by the TMA unit
+                            mbar_expect_tx(full, L.stage_x);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                tma_load_2d(base + L.x + (uint32_t)s * L.stage_x + (uint32_t)j * 4096u, &p.map_x, g.f0 + 32 * j,
+                                            (int)(g.row0 + kb * kKB), full);
                         } else {
                             const int k0 = (int)(kb * kKB);
+                            mbar_expect_tx(full, L.stage_x + L.stage_mu);
                             tma_load_2d(base + L.x + (uint32_t)s * L.stage_x, &p.map_x, k0, (int)g.row0, full);
-                            tma_load_2d(base + L.bhi + (uint32_t)s * L.stage_b, &p.map_bhi, k0, 0, full);
-                            tma_load_2d(base + L.blo + (uint32_t)s * L.stage_b, &p.map_blo, k0, 0, full);
                             bulk_load_1d(base + L.mu + (uint32_t)s * L.stage_mu, p.mu_pad + k0, 128, full);
+                        }
+                    }
+                }
+            }
+        } else if (warp == kTransformWarps + 3) {
+            // ================================ TMA producer: B ring ================================
+            if (lane == 0) {
+                uint32_t it = 0;
+                Group g;
+                for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
+                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                        const int sb = (int)(it % (uint32_t)SB);
+                        const uint32_t phb = (it / (uint32_t)SB) & 1u;
+                        mbar_wait(bar_empty_b(bars, sb), phb ^ 1u);
+                        const uint32_t fullb = bar_full_b(bars, sb);
+                        if (ATB && panel) {
+                            // panel-major Y: rows (r/32)*n_pad .. +n_pad of the [blocks*n_pad][32] views are exactly
+                            // the K-major Y_hi / Y_lo operand tiles
+                            const int r = (int)(g.row0 + kb * kKB);
+                            mbar_expect_tx(fullb, 2u * L.stage_b);
+                            tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, 0, (r / 32) * n_pad, fullb);
+                            tma_load_2d(base + L.blo + (uint32_t)sb * L.stage_b, &p.map_blo, 0, (r / 32) * n_pad, fullb);
+                        } else if (ATB) {
+                            // row-major Y: box {n_pad, 32 rows}, transposed + split by the transform warps
+                            mbar_expect_tx(fullb, L.stage_b);
+                            tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, 0, (int)(g.row0 + kb * kKB), fullb);
+                        } else {
+                            const int k0 = (int)(kb * kKB);
+                            mbar_expect_tx(fullb, 2u * L.stage_b);
+                            tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, k0, 0, fullb);
+                            tma_load_2d(base + L.blo + (uint32_t)sb * L.stage_b, &p.map_blo, k0, 0, fullb);
                         }
                     }
                 }
@@ -582,22 +666,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 mbar_wait(bar_acc_empty(bars), ((uint32_t)gi & 1u) ^ 1u);
                 tc_fence_after();
                 for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
-                    const int s = (int)(it % (uint32_t)S);
-                    const uint32_t ph = (it / (uint32_t)S) & 1u;
+                    const int sb = (int)(it % (uint32_t)SB);
+                    const uint32_t phb = (it / (uint32_t)SB) & 1u;
                     const int ta = (int)(it & 1u);
                     const uint32_t pa = (it >> 1) & 1u;
-                    // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are produced
-                    // by the transform warps together with the TMEM operand (a_ready covers both)
-                    if (!ATB) mbar_wait(bar_full(bars, s), ph);
+                    // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are produced (or, panel-major,
+                    // checked in) by the transform warps together with the TMEM operand (a_ready covers both)
+                    if (!ATB || panel) mbar_wait(bar_full_b(bars, sb), phb);
                     mbar_wait(bar_a_ready(bars, ta), pa);
                     tc_fence_after();
                     if (mt == 0 && lane == 0) trace_ev(p, 1, it);
                     // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
                     const int yb = (int)(it % (uint32_t)kYBufs);
-                    const uint32_t bhi_addr = ATB ? (base + L.ylo + (uint32_t)yb * L.ylo_bytes)
-                                                  : (base + L.bhi + (uint32_t)s * L.stage_b);
-                    const uint32_t blo_addr = ATB ? (bhi_addr + (uint32_t)n_pad * 128u)
-                                                  : (base + L.blo + (uint32_t)s * L.stage_b);
+                    const uint32_t ring = base + L.ylo + (uint32_t)yb * L.ylo_bytes;
+                    const bool from_ring = ATB && !panel;
+                    const uint32_t bhi_addr = from_ring ? ring : (base + L.bhi + (uint32_t)sb * L.stage_b);
+                    const uint32_t blo_addr = from_ring ? (ring + (uint32_t)n_pad * 128u) : (base + L.blo + (uint32_t)sb * L.stage_b);
                     const uint64_t dhi0 = make_desc_sw128(bhi_addr, 16u, 1024u);
                     const uint64_t dlo0 = make_desc_sw128(blo_addr, 16u, 1024u);
                     const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kAStageCols + mt * 64);
@@ -614,8 +698,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
                         }
                         tc_commit(bar_a_free(bars, ta));
-                        if (!ATB) tc_commit(bar_empty_b(bars, s));
-                        else tc_commit(bar_y_free(bars, yb));
+                        if (!ATB || panel) tc_commit(bar_empty_b(bars, sb));
+                        if (ATB && !panel) tc_commit(bar_y_free(bars, yb));
                     }
                     __syncwarp();
                     if (mt == 0 && lane == 0) trace_ev(p, 2, it);
@@ -745,12 +829,14 @@ inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t sm
 
 // Y[n x ldy] = (A - mu) * B.  B: TS in {float, double}, K x L row-major (ldb) or L x K when b_trans.
 // Columns [L, min(ldy, n_pad)) of Y are written as zeros (padding for later TMA reads).
+// y_panel: Y is written panel-major, [ceil(n/32)][n_pad][32] floats (n_pad = L rounded up to 16), rows >= n zero.
 template <typename TS>
 void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_t K, const TS* B, int64_t ldb,
-                  bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq) {
+                  bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq,
+                  bool y_panel = false, float* Y_lo_panel = nullptr) {
     const int n_pad = round_up(L, 16);
-    const int stages = pick_stages(false, n_pad);
-    if (stages < 2) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
+    int stages = 0, stages_b = 0;
+    if (!pick_stages(false, n_pad, false, stages, stages_b)) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
     const int64_t Kp = round_up(K, 32);
     DBuf<float> bhi(ctx, (size_t)(n_pad * Kp)), blo(ctx, (size_t)(n_pad * Kp)), mup(ctx, (size_t)Kp);
     prep_b_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * Kp, 256), 256, 0, ctx->stream>>>(B, ldb, b_trans ? 1 : 0, K, Kp,
@@ -769,11 +855,14 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     p.n_pad = n_pad;
     p.L = (int)L;
     p.stages = stages;
+    p.stages_b = stages_b;
     p.Y = Y;
     p.ldy = ldy;
     p.y_vec = (is_aligned16(Y) && (ldy % 4 == 0)) ? 1 : 0;
+    p.y_panel = y_panel ? 1 : 0;
+    p.Ylo = Y_lo_panel;
     p.sumsq = sumsq;
-    const SmemLayout lay = make_layout(false, n_pad, stages);
+    const SmemLayout lay = make_layout(false, n_pad, stages, stages_b);
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
     KTimer kt(ctx, K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny", (double)n * (K + L) * sizeof(float));
@@ -786,11 +875,13 @@ inline bool atb_supported(const void* A, int64_t lda, int64_t da, const void* B,
 }
 
 // Z[da x ldz] (f64, accumulated; caller zeroes) += (A - mua)^T * B, B is n x db (ldb), not centred.
+// b_panel: B is panel-major [ceil(n/32)][n_pad][32] (as written by launch_tc_xb with y_panel).
 inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t da, const float* mua, const float* B,
-                          int64_t ldb, int64_t db, int64_t n, double* Z, int64_t ldz) {
+                          int64_t ldb, int64_t db, int64_t n, double* Z, int64_t ldz, bool b_panel = false,
+                          const float* B_lo_panel = nullptr) {
     const int n_pad = round_up(db, 16);
-    const int stages = pick_stages(true, n_pad);
-    if (stages < 2) linalg_error("tc_atb: no pipeline configuration fits in shared memory");
+    int stages = 0, stages_b = 0;
+    if (!pick_stages(true, n_pad, b_panel, stages, stages_b)) linalg_error("tc_atb: no pipeline configuration fits in shared memory");
     const int fgroups = (int)ceil_div(da, 256);
     const int64_t Fp = (int64_t)fgroups * 256;
     DBuf<float> mup(ctx, (size_t)Fp);
@@ -798,15 +889,22 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     check_launch(ctx);
     TcParams p;
     std::memset(&p, 0, sizeof p);
-    p.map_x = make_map_2d(A, (uint64_t)da, (uint64_t)n, (uint64_t)lda, 256, 32, false);
-    p.map_bhi = make_map_2d(B, (uint64_t)db, (uint64_t)n, (uint64_t)ldb, (uint32_t)n_pad, 32, false);
-    p.map_blo = p.map_bhi;
+    p.map_x = make_map_2d(A, (uint64_t)da, (uint64_t)n, (uint64_t)lda, 32, 32, true);
+    if (b_panel) {
+        p.map_bhi = make_map_2d(B, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
+        p.map_blo = make_map_2d(B_lo_panel, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
+    } else {
+        p.map_bhi = make_map_2d(B, (uint64_t)db, (uint64_t)n, (uint64_t)ldb, (uint32_t)n_pad, 32, false);
+        p.map_blo = p.map_bhi;
+    }
+    p.y_panel = b_panel ? 1 : 0;
     p.mu_pad = mup.p;
     p.n = n;
     p.K = da;
     p.n_pad = n_pad;
     p.L = (int)db;
     p.stages = stages;
+    p.stages_b = stages_b;
     p.Z = Z;
     p.ldz = ldz;
     // One CTA = one feature group x one contiguous slice of rows; the TMEM accumulation chain is cut
@@ -817,7 +915,7 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.slice_rows = ceil_div(ceil_div(n, slices), 32) * 32;
     p.fgroups = fgroups;
     p.dbg = 0;
-    const SmemLayout lay = make_layout(true, n_pad, stages);
+    const SmemLayout lay = make_layout(true, n_pad, stages, stages_b, b_panel);
     const int grid = (int)(ceil_div(n, p.slice_rows) * fgroups);
     KTimer kt(ctx, da >= 256 ? "tc_atb_f32" : "tc_atb_f32_skinny", (double)n * (da + db) * sizeof(float));
     switch (n_pad) {

@@ -466,3 +466,25 @@ def test_two_gpu_row_sharding(pd):
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n,d", [(1000, 64), (4097, 100), (3000, 260), (513, 129)])
+def test_dmma_gram_engines(pd, n, d):
+    """Centred f64 Gram through the DMMA (mma.sync f64) kernel and through the DFMA kernel."""
+    x = synth.gaussian(n, d, seed=n + d)
+    ctx = pd.default_context()
+    outs = {}
+    for eng in (0, 1):
+        ctx.set_f64_engine(eng)
+        outs[eng] = pd.colmean_gram(x)[1]
+    ctx.set_f64_engine(1)
+    mean = x.mean(axis=0)
+    ref = (x - mean).T @ (x - mean)
+    for eng in (0, 1):
+        assert np.allclose(outs[eng], ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    y = synth.gaussian(n, 96, seed=3)
+    for eng in (0, 1):
+        ctx.set_f64_engine(eng)
+        z = pd.xty(x, y, mean)
+        assert np.allclose(z, (x - mean).T @ y, rtol=1e-12, atol=1e-11 * n)
+    ctx.set_f64_engine(1)
