@@ -33,8 +33,9 @@ constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
 constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
 constexpr int kTmemCols = 512;
 constexpr int kYBufs = 3;         // tc_atb: ring of transposed Y tiles (decoupled from the 2 TMEM operand stages)
-constexpr int kAStageCols = kMT * 64;  // per TMEM operand stage: MT x (32 hi + 32 lo) columns
-constexpr int kAccBase = 2 * kAStageCols;  // accumulators start after the two operand stages (256)
+constexpr int kASlots = 4;                 // TMEM operand ring: one slot per half K block (16 k-values)
+constexpr int kASlotCols = kMT * 32;       // per slot: MT x (16 hi + 16 lo) columns
+constexpr int kAccBase = kASlots * kASlotCols;  // accumulators start after the operand ring (256)
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -249,11 +250,11 @@ __device__ __forceinline__ uint32_t bar_full(uint32_t base, int s) { return base
 __device__ __forceinline__ uint32_t bar_empty_x(uint32_t base, int s) { return base + 8u * (8 + (uint32_t)s); }
 __device__ __forceinline__ uint32_t bar_full_b(uint32_t base, int s) { return base + 8u * (16 + (uint32_t)s); }   // B ring
 __device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (24 + (uint32_t)s); }
-__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (34 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 36; }
-__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 37; }
-__device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (40 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }  // 4 slots
+__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (36 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 40; }
+__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 41; }
+__device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (44 + (uint32_t)t); }
 
 // ------------------------------------------------------------------------------------------
 // the kernel (ATB = false: tc_xb, ATB = true: tc_atb; NP = compile-time n_pad for tc_atb)
@@ -310,29 +311,32 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 // transform + epilogue role (warps 0 .. 15).  warp w: M tile (w >> 2) & 1, TMEM lane quarter w & 3,
 // K-block half w >> 3.  EPI: this warp also runs the epilogue (tc_xb: all; tc_atb: first half only -
 // they hold the register accumulators, hence the separate instantiation and register budget).
-template <bool ATB, int NP, bool EPI>
+template <bool ATB, int NP, bool PANEL>
 __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_ptr, const SmemLayout& L,
                                                uint32_t bars, uint32_t tmem_base, int warp, int lane, int n_pad,
                                                int S) {
     {
         const int half = warp >> 3;
-        constexpr bool epi = EPI;  // warps that run the epilogue
+        constexpr bool epi = true;  // every transform warp also runs the epilogue
         const int mt = (warp >> 2) & 1;
         const int q = warp & 3;
         const int lrow = q * 32 + lane;           // lane (= row / feature) inside the M tile
         const uint32_t lane_field = (uint32_t)(q * 32) << 16;
         const int ttid = threadIdx.x;             // 0 .. 511
-        const bool panel = p.y_panel != 0;
+        constexpr bool panel = PANEL;
         uint32_t it = 0;
         double ss = 0.0;
-        float racc[(ATB && EPI) ? NP : 1];
+        // tc_atb: the two warps of a lane-quarter pair split the accumulator columns in alternate 16-column chunks,
+        // so each thread keeps at most ceil(NP/32) * 16 running sums in registers
+        constexpr int kAccChunks = ATB ? (NP / 16 + 1) / 2 : 1;
+        float racc[kAccChunks * 16];
 #pragma unroll
-        for (int j = 0; j < ((ATB && EPI) ? NP : 1); ++j) racc[j] = 0.f;
+        for (int j = 0; j < kAccChunks * 16; ++j) racc[j] = 0.f;
         // tc_atb: this thread's share of the Y-tile transposition (loop invariant): chunk i covers
         // column nn = i % n_pad, K rows 4*cc .. 4*cc+3 with cc = i / n_pad
-        constexpr int kYIter = ATB ? (NP * 8 + kTransformWarps * 32 - 1) / (kTransformWarps * 32) : 1;
+        constexpr int kYIter = (ATB && !PANEL) ? (NP * 8 + kTransformWarps * 32 - 1) / (kTransformWarps * 32) : 1;
         int y_src[kYIter], y_dst[kYIter];
-        if (ATB) {
+        if (ATB && !PANEL) {
 #pragma unroll
             for (int u = 0; u < kYIter; ++u) {
                 const int i = ttid + u * kTransformWarps * 32;
@@ -351,8 +355,9 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
             for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
                 const int s = (int)(it % (uint32_t)S);
                 const uint32_t ph = (it / (uint32_t)S) & 1u;
-                const int ta = (int)(it & 1u);
-                const uint32_t pa = (it >> 1) & 1u;
+                const uint32_t gran = 2u * it + (uint32_t)half;  // this warp's half K block
+                const int ta = (int)(gran & (kASlots - 1));
+                const uint32_t pa = (gran / kASlots) & 1u;
                 mbar_wait(bar_full(bars, s), ph);
                 if (warp == 0 && lane == 0) trace_ev(p, 3, it);
                 uint32_t v[16];
@@ -431,19 +436,19 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_empty_b(bars, sb));  // TMA-landed Y tile consumed
                 }
-                // TMEM operand stage `ta` must have been drained by the MMAs of two K blocks ago
+                // TMEM operand slot `ta` must have been drained by the MMAs of two K blocks ago
                 if (warp == 0 && lane == 0) trace_ev(p, 4, it);
                 mbar_wait(bar_a_free(bars, ta), pa ^ 1u);
                 tc_fence_after();
                 if (warp == 0 && lane == 0) trace_ev(p, 5, it);
-                const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kAStageCols + mt * 64 + half * 16);
+                const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kASlotCols + mt * 32);
                 tmem_st16(a_addr, v);  // hi: the tensor core ignores the low 13 mantissa bits
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const float f = __uint_as_float(v[k]);
                     v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
                 }
-                tmem_st16(a_addr + 32u, v);  // lo = v - tf32(v), exact
+                tmem_st16(a_addr + 16u, v);  // lo = v - tf32(v), exact
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -457,14 +462,17 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 mbar_wait(bar_acc_full(bars), (uint32_t)gi & 1u);
                 tc_fence_after();
                 const uint32_t acc = tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad);
-                if constexpr (ATB && EPI) {
+                if constexpr (ATB) {
 #pragma unroll
-                    for (int c0 = 0; c0 < NP; c0 += 16) {
-                        uint32_t w[16];
-                        tmem_ld16(acc + (uint32_t)c0, w);
-                        tmem_ld_wait();
+                    for (int ch = 0; ch < kAccChunks; ++ch) {
+                        const int c0 = (2 * ch + half) * 16;
+                        if (c0 < NP) {
+                            uint32_t w[16];
+                            tmem_ld16(acc + (uint32_t)c0, w);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) racc[c0 + j] += __uint_as_float(w[j]);
+                            for (int j = 0; j < 16; ++j) racc[ch * 16 + j] += __uint_as_float(w[j]);
+                        }
                     }
                 } else if constexpr (!ATB) {
                     if (panel) {
@@ -537,14 +545,16 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
             }
         }
         if constexpr (ATB) {
-            if constexpr (EPI) {
-                // the CTA's partial (256 features x L) -> global f64 accumulator
-                const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
-                if (f < p.K) {
+            // the CTA's partial (256 features x L) -> global f64 accumulator
+            const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
+            if (f < p.K) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j)
-                        if (j < p.L) atomicAdd(&p.Z[f * p.ldz + j], (double)racc[j]);
-                }
+                for (int ch = 0; ch < kAccChunks; ++ch)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = (2 * ch + half) * 16 + j;
+                        if (c < p.L) atomicAdd(&p.Z[f * p.ldz + c], (double)racc[ch * 16 + j]);
+                    }
             }
         } else if (p.sumsq) {
 #pragma unroll
@@ -554,13 +564,13 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
     }
 }
 
-template <bool ATB, int NP>
+template <bool ATB, int NP, bool PANEL>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const int n_pad = ATB ? NP : p.n_pad;
-    const bool panel = p.y_panel != 0;
+    constexpr bool panel = PANEL;
     const SmemLayout L = make_layout(ATB, n_pad, p.stages, p.stages_b, ATB && panel);
     const uint32_t bars = base + L.bars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -576,13 +586,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             // released by the two MMA warps, or by the transform warps when they consume the raw row-major Y tile
             mbar_init(bar_empty_b(bars, s), (ATB && !panel) ? kTransformWarps : kMT);
         }
-        for (int t = 0; t < 2; ++t) {
-            mbar_init(bar_a_ready(bars, t), kTransformWarps);
+        for (int t = 0; t < kASlots; ++t) {
+            mbar_init(bar_a_ready(bars, t), kTransformWarps / 2);  // the 8 warps that own this half of a K block
             mbar_init(bar_a_free(bars, t), kMT);
         }
         mbar_init(bar_acc_full(bars), kMT);
         for (int t = 0; t < kYBufs; ++t) mbar_init(bar_y_free(bars, t), kMT);
-        mbar_init(bar_acc_empty(bars), ATB ? kEpilogueWarps : kTransformWarps);
+        mbar_init(bar_acc_empty(bars), kTransformWarps);
         fence_barrier_init();
     }
     if (warp == kTransformWarps + 3) tmem_alloc(base + L.tmem_slot, kTmemCols);
@@ -592,7 +602,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L.tmem_slot);
 
     if (warp >= kTransformWarps) {
-        if (ATB) reg_dealloc<40>();
         if (warp == kTransformWarps) {
             // ================================ TMA producer: X ring ================================
             if (lane == 0) {
@@ -668,14 +677,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
                     const int sb = (int)(it % (uint32_t)SB);
                     const uint32_t phb = (it / (uint32_t)SB) & 1u;
-                    const int ta = (int)(it & 1u);
-                    const uint32_t pa = (it >> 1) & 1u;
-                    // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are produced (or, panel-major,
-                    // checked in) by the transform warps together with the TMEM operand (a_ready covers both)
+                    // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are TMA-loaded panels, or
+                    // (row-major Y) produced by ALL transform warps - then both halves must have checked in first
                     if (!ATB || panel) mbar_wait(bar_full_b(bars, sb), phb);
-                    mbar_wait(bar_a_ready(bars, ta), pa);
-                    tc_fence_after();
-                    if (mt == 0 && lane == 0) trace_ev(p, 1, it);
+                    if (ATB && !panel) {
+                        mbar_wait(bar_a_ready(bars, (int)((2u * it) & (kASlots - 1))), ((2u * it) / kASlots) & 1u);
+                        mbar_wait(bar_a_ready(bars, (int)((2u * it + 1u) & (kASlots - 1))), ((2u * it + 1u) / kASlots) & 1u);
+                    }
                     // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
                     const int yb = (int)(it % (uint32_t)kYBufs);
                     const uint32_t ring = base + L.ylo + (uint32_t)yb * L.ylo_bytes;
@@ -684,22 +692,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const uint32_t blo_addr = from_ring ? (ring + (uint32_t)n_pad * 128u) : (base + L.blo + (uint32_t)sb * L.stage_b);
                     const uint64_t dhi0 = make_desc_sw128(bhi_addr, 16u, 1024u);
                     const uint64_t dlo0 = make_desc_sw128(blo_addr, 16u, 1024u);
-                    const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kAStageCols + mt * 64);
-                    if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            // 32 B (= 2 descriptor address units) per K step inside the 128 B swizzle row
-                            const uint64_t dhi = dhi0 + (uint64_t)(ks * 2);
-                            const uint64_t dlo = dlo0 + (uint64_t)(ks * 2);
-                            const uint32_t a_hi = a_hi0 + (uint32_t)ks * 8u;
-                            const uint32_t a_lo = a_hi + 32u;
-                            mma_tf32_ts(acc, a_lo, dhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-                            mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
-                            mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t gran = 2u * it + (uint32_t)h;
+                        const int ta = (int)(gran & (kASlots - 1));
+                        if (!ATB || panel) mbar_wait(bar_a_ready(bars, ta), (gran / kASlots) & 1u);
+                        tc_fence_after();
+                        if (h == 0 && mt == 0 && lane == 0) trace_ev(p, 1, it);
+                        const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kASlotCols + mt * 32);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k2 = 0; k2 < ((p.dbg & 2) ? 0 : 2); ++k2) {
+                                const int ks = 2 * h + k2;
+                                // 32 B (= 2 descriptor address units) per K step inside the 128 B swizzle row
+                                const uint64_t dhi = dhi0 + (uint64_t)(ks * 2);
+                                const uint64_t dlo = dlo0 + (uint64_t)(ks * 2);
+                                const uint32_t a_hi = a_hi0 + (uint32_t)k2 * 8u;
+                                const uint32_t a_lo = a_hi + 16u;
+                                mma_tf32_ts(acc, a_lo, dhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                                mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
+                                mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
+                            }
+                            tc_commit(bar_a_free(bars, ta));
+                            if (h == 1) {
+                                if (!ATB || panel) tc_commit(bar_empty_b(bars, sb));
+                                if (ATB && !panel) tc_commit(bar_y_free(bars, yb));
+                            }
                         }
-                        tc_commit(bar_a_free(bars, ta));
-                        if (!ATB || panel) tc_commit(bar_empty_b(bars, sb));
-                        if (ATB && !panel) tc_commit(bar_y_free(bars, yb));
+                        __syncwarp();
                     }
                     __syncwarp();
                     if (mt == 0 && lane == 0) trace_ev(p, 2, it);
@@ -710,17 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
     } else {
         // ================================ transform + epilogue ================================
-        if (ATB) {
-            if (warp < kEpilogueWarps) {
-                reg_alloc<144>();
-                transform_role<ATB, NP, true>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
-            } else {
-                reg_dealloc<72>();
-                transform_role<ATB, NP, false>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
-            }
-        } else {
-            transform_role<ATB, NP, true>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
-        }
+        transform_role<ATB, NP, PANEL>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
     }
 
     tc_fence_before();
@@ -792,16 +802,16 @@ inline bool xb_supported(const void* A, int64_t lda, int64_t n, int64_t K, int64
            K < ((int64_t)1 << 31);
 }
 
-template <bool ATB, int NP>
+template <bool ATB, int NP, bool PANEL>
 inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t smem) {
     static size_t cur = 0;
     if (smem > cur) {
-        PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP, PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
     const char* trace_path = getenv("PETAL_TC_TRACE");
     if (trace_path == nullptr) {
-        tc_gemm_kernel<ATB, NP><<<grid, kThreads, smem, ctx->stream>>>(p);
+        tc_gemm_kernel<ATB, NP, PANEL><<<grid, kThreads, smem, ctx->stream>>>(p);
         check_launch(ctx);
         return;
     }
@@ -811,7 +821,7 @@ inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t sm
     DBuf<long long> tr(ctx, cnt);
     tr.zero();
     q.trace = tr.p;
-    tc_gemm_kernel<ATB, NP><<<grid, kThreads, smem, ctx->stream>>>(q);
+    tc_gemm_kernel<ATB, NP, PANEL><<<grid, kThreads, smem, ctx->stream>>>(q);
     check_launch(ctx);
     std::vector<long long> h(cnt);
     PETAL_CUDA(cudaMemcpyAsync(h.data(), tr.p, cnt * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -866,7 +876,8 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
     KTimer kt(ctx, K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny", (double)n * (K + L) * sizeof(float));
-    launch_kernel<false, 0>(ctx, p, grid, lay.total);
+    if (y_panel) launch_kernel<false, 0, true>(ctx, p, grid, lay.total);
+    else launch_kernel<false, 0, false>(ctx, p, grid, lay.total);
 }
 
 inline bool atb_supported(const void* A, int64_t lda, int64_t da, const void* B, int64_t ldb, int64_t db, int64_t n) {
@@ -914,19 +925,19 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.chunk_rows = 1024;
     p.slice_rows = ceil_div(ceil_div(n, slices), 32) * 32;
     p.fgroups = fgroups;
-    p.dbg = 0;
+    p.dbg = getenv("PETAL_TC_DBG") ? atoi(getenv("PETAL_TC_DBG")) : 0;
     const SmemLayout lay = make_layout(true, n_pad, stages, stages_b, b_panel);
     const int grid = (int)(ceil_div(n, p.slice_rows) * fgroups);
     KTimer kt(ctx, da >= 256 ? "tc_atb_f32" : "tc_atb_f32_skinny", (double)n * (da + db) * sizeof(float));
     switch (n_pad) {
-        case 16: launch_kernel<true, 16>(ctx, p, grid, lay.total); break;
-        case 32: launch_kernel<true, 32>(ctx, p, grid, lay.total); break;
-        case 48: launch_kernel<true, 48>(ctx, p, grid, lay.total); break;
-        case 64: launch_kernel<true, 64>(ctx, p, grid, lay.total); break;
-        case 80: launch_kernel<true, 80>(ctx, p, grid, lay.total); break;
-        case 96: launch_kernel<true, 96>(ctx, p, grid, lay.total); break;
-        case 112: launch_kernel<true, 112>(ctx, p, grid, lay.total); break;
-        default: launch_kernel<true, 128>(ctx, p, grid, lay.total); break;
+        case 16: if (b_panel) launch_kernel<true, 16, true>(ctx, p, grid, lay.total); else launch_kernel<true, 16, false>(ctx, p, grid, lay.total); break;
+        case 32: if (b_panel) launch_kernel<true, 32, true>(ctx, p, grid, lay.total); else launch_kernel<true, 32, false>(ctx, p, grid, lay.total); break;
+        case 48: if (b_panel) launch_kernel<true, 48, true>(ctx, p, grid, lay.total); else launch_kernel<true, 48, false>(ctx, p, grid, lay.total); break;
+        case 64: if (b_panel) launch_kernel<true, 64, true>(ctx, p, grid, lay.total); else launch_kernel<true, 64, false>(ctx, p, grid, lay.total); break;
+        case 80: if (b_panel) launch_kernel<true, 80, true>(ctx, p, grid, lay.total); else launch_kernel<true, 80, false>(ctx, p, grid, lay.total); break;
+        case 96: if (b_panel) launch_kernel<true, 96, true>(ctx, p, grid, lay.total); else launch_kernel<true, 96, false>(ctx, p, grid, lay.total); break;
+        case 112: if (b_panel) launch_kernel<true, 112, true>(ctx, p, grid, lay.total); else launch_kernel<true, 112, false>(ctx, p, grid, lay.total); break;
+        default: if (b_panel) launch_kernel<true, 128, true>(ctx, p, grid, lay.total); else launch_kernel<true, 128, false>(ctx, p, grid, lay.total); break;
     }
 }
 
