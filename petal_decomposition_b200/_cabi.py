@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpetal_b200.so")
+LIB_PATH = os.environ.get("PETAL_B200_LIB", os.path.join(HERE, "libpetal_b200.so"))  # override: A/B testing of builds
 
 PETAL_OK, PETAL_INVALID_INPUT, PETAL_LINALG_ERROR = 0, 1, 2
 COMM_ID_BYTES = 128

@@ -1,0 +1,463 @@
+// Fused FastICA fixed-point pass on tcgen05 / TMEM (f32, d <= 64 features, nc <= 64 components):
+//
+//     U = (X - mu) W~^T          (reference: w.dot(input),            src/ica.rs:332)
+//     G = g(U),  gp = sum g'(U)  (reference: logcosh,                 src/ica.rs:383-398)
+//     H^T = (X - mu)^T G         (reference: gwtx.dot(&input.t()),    src/ica.rs:333)
+//
+// in ONE pass over X: a 128-row tile is pulled in by TMA once, used as the A operand of the first MMA
+// (lanes = rows) and, transposed through the transform warps, as the A operand of the second MMA
+// (lanes = features); G never leaves the SM (TMEM -> registers -> shared-memory operand tiles).
+// Both contractions are 3xTF32 (hi/lo split, fp32 accumulate in TMEM); the H accumulator chain is cut
+// every 8 tiles (1024 rows) into fp32 registers, and only the CTA's totals go to global memory (f64 atomics).
+//
+// Warp roles (32 warps):
+//   0-15  row warps     : lane quarter q = w & 3, 16-column group cq = w >> 2
+//                         transform-A (x - mu, hi/lo -> TMEM A1), epilogue-1 (U -> g -> smem G tiles, g' sums)
+//   16-31 with (w & 3) < 2: feature warps, q = w & 3 (features 0-63), row quarter rq = (w - 16) >> 2
+//                         transform-B (transposed x - mu, hi/lo -> TMEM A2), H flush into registers, final atomics
+//   18    TMA producer  (X tile ring; W~ operand tiles once)
+//   19    MMA issuer + TMEM allocation
+//   others idle
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace petal {
+namespace ica {
+
+using namespace tc;
+
+constexpr int kRows = 128;                 // rows per tile
+constexpr int kD = 64;                     // padded features
+constexpr int kNC = 64;                    // padded components
+constexpr int kThreadsIca = 1024;
+constexpr int kRowWarps = 16;                // warps 0-15
+constexpr int kFeatWarps = 8;                // warps 16-31 with (w & 3) < 2
+constexpr int kTmaWarp = 18, kMmaWarp = 19;
+constexpr int kXStage = kRows * kD * 4;    // 32 KB: two [128 rows][32 floats] SWIZZLE_128B sub-tiles
+constexpr int kXStages = 3;
+constexpr int kWTile = kNC * 128;          // 8 KB: [64 comps][32 k] K-major SWIZZLE_128B
+constexpr int kGTile = kNC * 128;          // 8 KB: [64 comps][32 rows]
+constexpr int kFlushTiles = 8;
+// TMEM columns
+constexpr int kA1 = 0;                     // [hi 64 | lo 64]        lanes = rows
+constexpr int kA2 = 128;                   // [hi 128 | lo 128]      lanes = features
+constexpr int kAccU = 384;                 // 64 columns
+constexpr int kAccH = 448;                 // 64 columns
+
+struct IcaParams {
+    CUtensorMap map_x;    // X as {features inner, rows}, box {32, 128}, SWIZZLE_128B
+    CUtensorMap map_whi;  // W~ hi as {k inner (64), comps (64)}, box {32, 64}, SWIZZLE_128B
+    CUtensorMap map_wlo;
+    const float* mu_pad;  // [64]
+    int64_t n;
+    int d, nc, fun;
+    double* Ht;           // [d x nc] f64, accumulated
+    double* gp;           // [nc] f64, accumulated
+    long long* trace;     // optional clock64 timeline of CTA 0 (PETAL_ICA_TRACE)
+};
+
+// smem carve-up (offsets from a 1024 B aligned base)
+constexpr uint32_t kOffX = 0;
+constexpr uint32_t kOffW = kOffX + kXStages * kXStage;       // W hi: 2 tiles, W lo: 2 tiles
+constexpr uint32_t kOffG = kOffW + 4 * kWTile;               // G hi: 4 tiles, G lo: 4 tiles
+constexpr uint32_t kOffMu = kOffG + 8 * kGTile;
+constexpr uint32_t kOffBars = kOffMu + 256;
+constexpr uint32_t kOffSlot = kOffBars + 32 * 8;
+constexpr uint32_t kSmemIca = kOffSlot + 16 + 1024;
+
+__device__ __forceinline__ uint32_t ib(uint32_t bars, int i) { return bars + 8u * (uint32_t)i; }
+// barrier ids
+constexpr int B_XFULL = 0, B_XEMPTY = 3, B_WFULL = 6, B_A1 = 7, B_A2 = 8, B_UFULL = 9, B_UEMPTY = 10, B_GREADY = 11,
+              B_TILEFREE = 12, B_HFULL = 13, B_HEMPTY = 14;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// g(u) and the quantity summed per component.  For logcosh the kernel sums g^2 (sum g' = rows - sum g^2, one FFMA
+// instead of two); rows past n have u == 0 exactly, which gives g == 0 for every contrast function.
+template <int FUN>
+__device__ __forceinline__ float ica_g_acc(float u, float& acc) {
+    if (FUN == PETAL_ICA_LOGCOSH) {
+        // tanh(u) = sign(u) (1 - 2 / (exp(2|u|) + 1)): two MUFU ops, absolute error ~1e-7, saturates cleanly
+        const float e = ex2_approx(fabsf(u) * 2.8853900817779268f);
+        const float t = fmaf(-2.0f, rcp_approx(e + 1.0f), 1.0f);
+        const float g = copysignf(t, u);
+        acc = fmaf(g, g, acc);
+        return g;
+    } else if (FUN == PETAL_ICA_EXP) {
+        const float u2 = u * u;
+        const float e = ex2_approx(u2 * -0.72134752044448170f);
+        acc = fmaf(1.0f - u2, e, acc);
+        return u * e;
+    } else {
+        const float u2 = u * u;
+        acc = fmaf(3.0f, u2, acc);
+        return u * u2;
+    }
+}
+
+constexpr int kTraceTiles = 64;
+constexpr int kTraceEv = 16;
+__device__ __forceinline__ void ica_trace(const IcaParams& p, int ev, uint32_t it) {
+    if (p.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceTiles) p.trace[ev * kTraceTiles + it] = clock64();
+}
+
+template <int FUN>
+__global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_constant__ IcaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + kOffBars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = (p.n + kRows - 1) / kRows;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kXStages; ++s) {
+            mbar_init(ib(bars, B_XFULL + s), 1);
+            mbar_init(ib(bars, B_XEMPTY + s), kRowWarps + kFeatWarps);
+        }
+        mbar_init(ib(bars, B_WFULL), 1);
+        mbar_init(ib(bars, B_A1), kRowWarps);
+        mbar_init(ib(bars, B_A2), kFeatWarps);
+        mbar_init(ib(bars, B_UFULL), 1);
+        mbar_init(ib(bars, B_UEMPTY), kRowWarps);
+        mbar_init(ib(bars, B_GREADY), kRowWarps);
+        mbar_init(ib(bars, B_TILEFREE), 1);
+        mbar_init(ib(bars, B_HFULL), 1);
+        mbar_init(ib(bars, B_HEMPTY), kFeatWarps);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < kD; i += kThreadsIca) reinterpret_cast<float*>(bp + kOffMu)[i] = p.mu_pad[i];
+    if (warp == kMmaWarp) tmem_alloc(base + kOffSlot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(bp + kOffSlot);
+    const float* mus = reinterpret_cast<const float*>(bp + kOffMu);
+
+    if (warp == kTmaWarp) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            mbar_expect_tx(ib(bars, B_WFULL), 4 * kWTile);
+            for (int kb = 0; kb < 2; ++kb) {
+                tma_load_2d(base + kOffW + (uint32_t)kb * kWTile, &p.map_whi, kb * 32, 0, ib(bars, B_WFULL));
+                tma_load_2d(base + kOffW + (uint32_t)(2 + kb) * kWTile, &p.map_wlo, kb * 32, 0, ib(bars, B_WFULL));
+            }
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int s = (int)(it % kXStages);
+                mbar_wait(ib(bars, B_XEMPTY + s), ((it / kXStages) & 1u) ^ 1u);
+                mbar_expect_tx(ib(bars, B_XFULL + s), kXStage);
+                tma_load_2d(base + kOffX + (uint32_t)s * kXStage, &p.map_x, 0, (int)(t * kRows), ib(bars, B_XFULL + s));
+                tma_load_2d(base + kOffX + (uint32_t)s * kXStage + 16384u, &p.map_x, 32, (int)(t * kRows), ib(bars, B_XFULL + s));
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc_tf32(kNC, 0);
+        mbar_wait(ib(bars, B_WFULL), 0);
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const uint32_t ph = it & 1u;
+            const bool chain_start = (it % kFlushTiles) == 0;
+            const bool chain_end = ((it + 1) % kFlushTiles) == 0 || (t + gridDim.x >= ntiles);
+            // ---- MMA 1: U = A1 * W~^T
+            mbar_wait(ib(bars, B_A1), ph);
+            if (it > 0) mbar_wait(ib(bars, B_UEMPTY), (it - 1) & 1u);
+            tc_fence_after();
+            if (lane == 0) ica_trace(p, 9, it);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t woff = (uint32_t)(ks >> 2) * kWTile + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t dhi = make_desc_sw128(base + kOffW + woff, 16u, 1024u);
+                    const uint64_t dlo = make_desc_sw128(base + kOffW + 2u * kWTile + woff, 16u, 1024u);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kA1 + ks * 8);
+                    const uint32_t a_lo = a_hi + 64u;
+                    mma_tf32_ts(tmem_base + kAccU, a_lo, dhi, idesc, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(tmem_base + kAccU, a_hi, dlo, idesc, 1u);
+                    mma_tf32_ts(tmem_base + kAccU, a_hi, dhi, idesc, 1u);
+                }
+                tc_commit(ib(bars, B_UFULL));
+            }
+            __syncwarp();
+            if (lane == 0) ica_trace(p, 10, it);
+            // ---- MMA 2: H^T += A2 * G
+            mbar_wait(ib(bars, B_GREADY), ph);
+            mbar_wait(ib(bars, B_A2), ph);
+            if (chain_start && it > 0) mbar_wait(ib(bars, B_HEMPTY), ((it / kFlushTiles) - 1) & 1u);
+            tc_fence_after();
+            if (lane == 0) ica_trace(p, 11, it);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    const uint32_t goff = (uint32_t)(ks >> 2) * kGTile + (uint32_t)(ks & 3) * 32u;
+                    const uint64_t dhi = make_desc_sw128(base + kOffG + goff, 16u, 1024u);
+                    const uint64_t dlo = make_desc_sw128(base + kOffG + 4u * kGTile + goff, 16u, 1024u);
+                    const uint32_t a_hi = tmem_base + (uint32_t)(kA2 + ks * 8);
+                    const uint32_t a_lo = a_hi + 128u;
+                    mma_tf32_ts(tmem_base + kAccH, a_lo, dhi, idesc, (chain_start && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(tmem_base + kAccH, a_hi, dlo, idesc, 1u);
+                    mma_tf32_ts(tmem_base + kAccH, a_hi, dhi, idesc, 1u);
+                }
+                tc_commit(ib(bars, B_TILEFREE));
+                if (chain_end) tc_commit(ib(bars, B_HFULL));
+            }
+            __syncwarp();
+            if (lane == 0) ica_trace(p, 12, it);
+        }
+    } else if (warp < kRowWarps) {
+        // ================================ row warps ================================
+        const int q = warp & 3, cq = warp >> 2;           // lane quarter, 16-column group
+        const int r = q * 32 + lane;                      // row inside the tile = TMEM lane
+        const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+        const bool tr = (warp == 0 && lane == 0);
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        int nvalid = 0;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = (int)(it % kXStages);
+            const uint32_t ph = it & 1u;
+            const bool valid = t * kRows + r < p.n;
+            nvalid += valid ? 1 : 0;
+            // ---- transform-A: this thread's row, features 16*cq .. 16*cq+15
+            mbar_wait(ib(bars, B_XFULL + s), (it / kXStages) & 1u);
+            if (tr) ica_trace(p, 0, it);
+            uint32_t v[16];
+            {
+                const uint8_t* xr = bp + kOffX + (uint32_t)s * kXStage + (uint32_t)(cq >> 1) * 16384u + r * 128;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    const int c = (cq & 1) * 4 + c4;
+                    const float4 x4 = *reinterpret_cast<const float4*>(xr + ((c ^ (r & 7)) << 4));
+                    const float4 m4 = *reinterpret_cast<const float4*>(mus + cq * 16 + c4 * 4);
+                    v[c4 * 4 + 0] = __float_as_uint(valid ? x4.x - m4.x : 0.f);
+                    v[c4 * 4 + 1] = __float_as_uint(valid ? x4.y - m4.y : 0.f);
+                    v[c4 * 4 + 2] = __float_as_uint(valid ? x4.z - m4.z : 0.f);
+                    v[c4 * 4 + 3] = __float_as_uint(valid ? x4.w - m4.w : 0.f);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ib(bars, B_XEMPTY + s));
+            // A1 is free: MMA 1 of the previous tile completed before this warp passed u_full(t-1)
+            {
+                const uint32_t a = tmem_base + lane_field + (uint32_t)(kA1 + cq * 16);
+                tmem_st16(a, v);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float f = __uint_as_float(v[k]);
+                    v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
+                }
+                tmem_st16(a + 64u, v);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ib(bars, B_A1));
+            }
+            if (tr) ica_trace(p, 1, it);
+            // ---- epilogue-1: U[r][16*cq ..] -> g
+            mbar_wait(ib(bars, B_UFULL), ph);
+            tc_fence_after();
+            if (tr) ica_trace(p, 2, it);
+            {
+                tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccU + cq * 16), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ib(bars, B_UEMPTY));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(ica_g_acc<FUN>(__uint_as_float(v[j]), acc[j]));
+            if (tr) ica_trace(p, 3, it);
+            // G tiles are free once MMA 2 of the previous tile has completed
+            if (it > 0) mbar_wait(ib(bars, B_TILEFREE), (it - 1) & 1u);
+            if (tr) ica_trace(p, 4, it);
+            {
+                // K-major operand tiles [comp][32 rows] per 32-row block (= q), SWIZZLE_128B
+                uint8_t* gh = bp + kOffG + (uint32_t)q * kGTile + (lane & 3) * 4;
+                const int rc = lane >> 2;  // 16 B chunk of this row inside the 128 B line
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = cq * 16 + j;
+                    const int off = c * 128 + ((rc ^ (j & 7)) << 4);   // (c & 7) == (j & 7)
+                    const float g = __uint_as_float(v[j]);
+                    *reinterpret_cast<float*>(gh + off) = g;
+                    *reinterpret_cast<float*>(gh + 4u * kGTile + off) = g - __uint_as_float(v[j] & 0xFFFFE000u);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ib(bars, B_GREADY));
+            }
+            if (tr) ica_trace(p, 5, it);
+        }
+        // per-column totals of this warp's rows -> sum of g' -> one atomic per column per warp
+        const float fvalid = (float)nvalid, finvalid = (float)((int)it - nvalid);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float sgp = acc[j];
+            if (FUN == PETAL_ICA_LOGCOSH) sgp = fvalid - sgp;        // sum (1 - g^2) over valid rows
+            else if (FUN == PETAL_ICA_EXP) sgp = sgp - finvalid;     // u == 0 rows contributed exactly 1 each
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sgp += __shfl_xor_sync(0xffffffffu, sgp, o);
+            const int c = cq * 16 + j;
+            if (lane == 0 && c < p.nc) atomicAdd(&p.gp[c], (double)sgp);
+        }
+    } else if ((warp & 3) < 2) {
+        // ================================ feature warps ================================
+        const int q = warp & 3;                      // 0, 1: features 0-31, 32-63
+        const int rq = (warp - kRowWarps) >> 2;      // rows 32*rq .. 32*rq+31 of the tile; H columns 16*rq .. +15
+        const int f = q * 32 + lane;
+        const uint32_t lane_field = (uint32_t)(q * 32) << 16;
+        const float mu_f = mus[f];
+        const bool tr = (warp == kRowWarps && lane == 0);
+        float racc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) racc[j] = 0.f;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = (int)(it % kXStages);
+            mbar_wait(ib(bars, B_XFULL + s), (it / kXStages) & 1u);
+            if (tr) ica_trace(p, 6, it);
+            const uint8_t* xs = bp + kOffX + (uint32_t)s * kXStage + (uint32_t)(f >> 5) * 16384u + (f & 3) * 4;
+            const int fc = (f & 31) >> 2;
+            uint32_t v0[16], v1[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int row = rq * 32 + k;
+                v0[k] = __float_as_uint(*reinterpret_cast<const float*>(xs + row * 128 + ((fc ^ (row & 7)) << 4)) - mu_f);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int row = rq * 32 + 16 + k;
+                v1[k] = __float_as_uint(*reinterpret_cast<const float*>(xs + row * 128 + ((fc ^ (row & 7)) << 4)) - mu_f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ib(bars, B_XEMPTY + s));
+            // A2 is free once MMA 2 of the previous tile has completed
+            if (it > 0) mbar_wait(ib(bars, B_TILEFREE), (it - 1) & 1u);
+            tc_fence_after();
+            if (tr) ica_trace(p, 7, it);
+            const uint32_t a = tmem_base + lane_field + (uint32_t)(kA2 + rq * 32);
+            tmem_st16(a, v0);
+            tmem_st16(a + 16u, v1);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                v0[k] = __float_as_uint(__uint_as_float(v0[k]) - __uint_as_float(v0[k] & 0xFFFFE000u));
+                v1[k] = __float_as_uint(__uint_as_float(v1[k]) - __uint_as_float(v1[k] & 0xFFFFE000u));
+            }
+            tmem_st16(a + 128u, v0);
+            tmem_st16(a + 144u, v1);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ib(bars, B_A2));
+            if (tr) ica_trace(p, 8, it);
+            // ---- H flush: every feature warp reads out its 16 columns
+            const bool chain_end = ((it + 1) % kFlushTiles) == 0 || (t + gridDim.x >= ntiles);
+            if (chain_end) {
+                mbar_wait(ib(bars, B_HFULL), (it / kFlushTiles) & 1u);
+                tc_fence_after();
+                uint32_t w[16];
+                tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccH + rq * 16), w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) racc[j] += __uint_as_float(w[j]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ib(bars, B_HEMPTY));
+            }
+        }
+        if (f < p.d) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = rq * 16 + j;
+                if (c < p.nc) atomicAdd(&p.Ht[(size_t)f * p.nc + c], (double)racc[j]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+inline bool fused_supported(const void* X, int64_t ld, int64_t n, int64_t d, int64_t nc) {
+    return n >= 1024 && d >= 4 && d <= kD && nc >= 1 && nc <= kNC && (ld % 4 == 0) && is_aligned16(X) && n < ((int64_t)1 << 31);
+}
+
+// One fused pass: Ht[d x nc] += (X - mu)^T g((X - mu) Wt^T), gp[nc] += sum g'(.).  Wt is nc x d (f32, row-major).
+// Ht and gp must be zeroed by the caller.
+inline void launch_ica_fused(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, const float* mu,
+                             const float* Wt, int64_t nc, int fun, double* Ht, double* gp) {
+    DBuf<float> whi(ctx, (size_t)(kNC * kD)), wlo(ctx, (size_t)(kNC * kD)), mup(ctx, (size_t)kD);
+    // Bt[c][k] = Wt[c][k]  (operand tiles want [component][feature], K contiguous) -> "b_trans" view of an L x K matrix
+    prep_b_kernel<float><<<(unsigned)ceil_div((int64_t)kNC * kD, 256), 256, 0, ctx->stream>>>(Wt, d, 1, d, kD, (int)nc, kNC,
+                                                                                               whi.p, wlo.p);
+    check_launch(ctx);
+    prep_mu_kernel<<<1, 256, 0, ctx->stream>>>(mu, d, kD, mup.p);
+    check_launch(ctx);
+    IcaParams p;
+    std::memset(&p, 0, sizeof p);
+    p.map_x = make_map_2d(X, (uint64_t)d, (uint64_t)n, (uint64_t)ld, 32, kRows, true);
+    p.map_whi = make_map_2d(whi.p, kD, kNC, kD, 32, kNC, true);
+    p.map_wlo = make_map_2d(wlo.p, kD, kNC, kD, 32, kNC, true);
+    p.mu_pad = mup.p;
+    p.n = n;
+    p.d = (int)d;
+    p.nc = (int)nc;
+    p.fun = fun;
+    p.Ht = Ht;
+    p.gp = gp;
+    long long* trace = nullptr;
+    DBuf<long long> trbuf;
+    if (getenv("PETAL_ICA_TRACE")) {
+        trbuf.alloc(ctx, (size_t)kTraceEv * kTraceTiles);
+        trbuf.zero();
+        trace = trbuf.p;
+    }
+    p.trace = trace;
+    const int64_t ntiles = ceil_div(n, kRows);
+    const int grid = (int)std::min<int64_t>(ntiles, ctx->sm_count);
+    auto launch = [&](auto kernel) {
+        PETAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemIca));
+        KTimer kt(ctx, "ica_fused_f32", (double)n * d * sizeof(float));
+        kernel<<<grid, kThreadsIca, kSmemIca, ctx->stream>>>(p);
+        check_launch(ctx);
+    };
+    if (fun == PETAL_ICA_LOGCOSH) launch(ica_fused_kernel<PETAL_ICA_LOGCOSH>);
+    else if (fun == PETAL_ICA_EXP) launch(ica_fused_kernel<PETAL_ICA_EXP>);
+    else launch(ica_fused_kernel<PETAL_ICA_CUBE>);
+    if (trace) {
+        std::vector<long long> h((size_t)kTraceEv * kTraceTiles);
+        PETAL_CUDA(cudaMemcpyAsync(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        auto ev = [&](int e, int i) { return h[(size_t)e * kTraceTiles + i]; };
+        const int a = 8, b = (int)std::min<int64_t>(40, ceil_div(ntiles, grid) - 1);
+        if (b > a) {
+            auto mean = [&](int e1, int e0, int sh) {
+                double sacc = 0;
+                for (int i = a; i < b; ++i) sacc += (double)(ev(e1, i + sh) - ev(e0, i));
+                return sacc / (b - a);
+            };
+            fprintf(stderr,
+                    "[ica trace] period %.0f | row: xfull->a1 %.0f  a1->ufull %.0f  ufull->g %.0f  g->tilefree %.0f  tilefree->gready %.0f  "
+                    "gready->next xfull %.0f | feat: xfull->tilefree %.0f  tilefree->a2 %.0f | mma: a1got->m1 issued %.0f  m1->g/a2 got %.0f  "
+                    "->m2 issued %.0f  m2->next a1 got %.0f\n",
+                    mean(0, 0, 1), mean(1, 0, 0), mean(2, 1, 0), mean(3, 2, 0), mean(4, 3, 0), mean(5, 4, 0), mean(0, 5, 1),
+                    mean(7, 6, 0), mean(8, 7, 0), mean(10, 9, 0), mean(11, 10, 0), mean(12, 11, 0), mean(9, 12, 1));
+        }
+    }
+}
+
+}  // namespace ica
+}  // namespace petal

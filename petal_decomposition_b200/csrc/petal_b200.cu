@@ -10,6 +10,7 @@
 #include "small_linalg.cuh"
 #include "stream_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "ica_kernels.cuh"
 
 using namespace petal;
 
@@ -187,11 +188,21 @@ void compute_mean(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_to
 template <typename T>
 void centered_gram(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G) {
     PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
-    AtbParams<T> p{};
-    p.A = X; p.lda = ld; p.da = d; p.mua = mu;
-    p.B = X; p.ldb = ld; p.db = d; p.mub = mu;
-    p.n = n; p.C = G; p.ldc = d; p.symmetric = 1;
-    launch_atb<T>(ctx, p);
+    bool done = false;
+    if constexpr (sizeof(T) == 4) {
+        // narrow f32 Gram (d <= 128): one tcgen05 pass, both operands centred on load
+        if (ctx->f32_engine == 1 && tc::atb_supported(X, ld, d, X, ld, d, n) && is_aligned16(mu)) {
+            tc::launch_tc_atb(ctx, X, ld, d, mu, X, ld, d, n, G, d, false, nullptr, mu);
+            done = true;
+        }
+    }
+    if (!done) {
+        AtbParams<T> p{};
+        p.A = X; p.lda = ld; p.da = d; p.mua = mu;
+        p.B = X; p.ldb = ld; p.db = d; p.mub = mu;
+        p.n = n; p.C = G; p.ldc = d; p.symmetric = 1;
+        launch_atb<T>(ctx, p);
+    }
     allreduce_sum(ctx, G, (size_t)(d * d));
     launch_symmetrize(ctx, G, d);
 }
@@ -690,7 +701,10 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
 
     // Gd -> X.  With whitening: HK = H K1^T = (Ht)^T (K1^T): stage Ht (d x nc) in Tm and K1^T (d x nc) in Y
     // (both need d <= nc-sized buffers: d <= kIcaFusedMax is checked by the host) and multiply in shared memory.
-    if (K1) {
+    if (Ht == nullptr) {
+        // initial symmetric decorrelation of w_init (src/ica.rs:329): polar factor of W itself
+        for (int e = tid; e < nc * nc; e += kIcaThreads) X[(e / nc) * ld + e % nc] = W[e];
+    } else if (K1) {
         for (int e = tid; e < d * nc; e += kIcaThreads) {
             const int f = e / nc, i = e % nc;
             Tm[f * ld + i] = Ht[e];                    // Ht[f][i]
@@ -819,6 +833,23 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
     }
 }
 
+// One-pass FastICA streaming kernel (ica_kernels.cuh): f32 only, d and nc <= 64, tcgen05 engine selected.
+template <typename T>
+bool ica_one_pass_supported(petal_ctx*, const T*, int64_t, int64_t, int64_t, int64_t) { return false; }
+template <>
+bool ica_one_pass_supported<float>(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, int64_t nc) {
+    if (const char* e = getenv("PETAL_ICA_ONEPASS")) if (e[0] == '0') return false;
+    return ctx->f32_engine == 1 && ica::fused_supported(X, ld, n, d, nc);
+}
+inline void ica_one_pass(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, const float* mu, const float* Wt,
+                         int64_t nc, int fun, double* Ht, double* gp) {
+    ica::launch_ica_fused(ctx, X, ld, n, d, mu, Wt, nc, fun, Ht, gp);
+}
+inline void ica_one_pass(petal_ctx*, const double*, int64_t, int64_t, int64_t, const double*, const double*, int64_t, int,
+                         double*, double*) {
+    linalg_error("one-pass FastICA kernel is f32 only");
+}
+
 // ica_par (reference src/ica.rs:319-361) on data X[n x d] with whitening folded in:
 // the whitened sample is x1 = K1 (x - mu) with K1 = sqrt(n) K (nc x d); K1 == nullptr means the
 // data is already white (d == nc).  Returns W (nc x nc, f64, device) and the iteration count.
@@ -827,10 +858,10 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
              int64_t nc, int fun, double tol, int64_t max_iter, int lim_variant, const double* w_init, double* W,
              int64_t* n_iter_out, double* lim_out) {
     if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
-    symmetric_decorrelation(ctx, w_init, nc, W);  // src/ica.rs:329
     DBuf<double> Wk(ctx, (size_t)(nc * d)), Hg(ctx, (size_t)(nc * d)), Htg(ctx, (size_t)(nc * d + nc)), HK(ctx, (size_t)(nc * nc)),
         Gd(ctx, (size_t)(nc * nc)), W1(ctx, (size_t)(nc * nc)), limd(ctx, 1);
-    DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, (size_t)(n * nc));
+    const bool one_pass = ica_one_pass_supported<T>(ctx, X, d, n, d, nc);
+    DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, one_pass ? (size_t)1 : (size_t)(n * nc));
     double* H = Hg.p;
     double* Ht = Htg.p;          // [H^T (d x nc) | sum g' (nc)] reduced across ranks together
     double* gp = Htg.p + nc * d;
@@ -856,16 +887,40 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
         }
         launch_cast<double, T>(ctx, Wfull, Wt.p, nc * d);
     };
-    make_wt();
+    // W = symmetric_decorrelation(w_init) (src/ica.rs:329) and the first W~
+    bool init_done = false;
+    if (fused) {
+        PETAL_CUDA(cudaMemcpyAsync(W, w_init, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        {
+            KTimer kt(ctx, "ica_update", 0.0);
+            ica_update_kernel<T><<<1, kIcaThreads, 3 * (size_t)nc * (nc + 1) * sizeof(double), ctx->stream>>>(
+                nullptr, nullptr, W, K1, (int)nc, (int)d, inv_n, lim_variant, Wt.p, out2.p);
+            launch1(ctx);
+        }
+        double h2[2] = {0.0, 1.0};
+        PETAL_CUDA(cudaMemcpyAsync(h2, out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        init_done = (h2[1] == 0.0);
+    }
+    if (!init_done) {
+        symmetric_decorrelation(ctx, w_init, nc, W);
+        make_wt();
+    }
     for (int64_t it = 0; it < max_iter; ++it) {
-        // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
-        gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
-        // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
-        PETAL_CUDA(cudaMemsetAsync(gp, 0, (size_t)nc * sizeof(double), ctx->stream));
-        launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp);
-        // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening],
-        // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
-        gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht);
+        if (one_pass) {
+            // U, g(U), sum g'(U) and H^T in a single pass over X (tcgen05; U and g(U) never reach HBM)
+            PETAL_CUDA(cudaMemsetAsync(Htg.p, 0, (size_t)(nc * d + nc) * sizeof(double), ctx->stream));
+            ica_one_pass(ctx, X, d, n, d, mu, Wt.p, nc, fun, Ht, gp);
+        } else {
+            // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
+            gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
+            // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
+            PETAL_CUDA(cudaMemsetAsync(gp, 0, (size_t)nc * sizeof(double), ctx->stream));
+            launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp);
+            // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening],
+            // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
+            gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht);
+        }
         allreduce_sum(ctx, Htg.p, (size_t)(nc * d + nc));
         bool done_small = false;
         if (fused) {

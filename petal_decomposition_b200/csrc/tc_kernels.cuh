@@ -180,6 +180,7 @@ struct TcParams {
                           // tc_atb: Y as {cols inner, rows}, box {n_pad, 32}, no swizzle
     CUtensorMap map_blo;  // tc_xb : B^T lo (same shape as hi); unused by tc_atb
     const float* mu_pad;  // tc_xb: [K rounded up to 32] zero padded; tc_atb: [features rounded up to 256]; never null
+    const float* mub_pad; // tc_atb, row-major Y only: column means of Y [n_pad] subtracted on load (nullable)
     int64_t n;            // rows
     int64_t K;            // tc_xb: reduction length (features); tc_atb: da (features)
     int n_pad;            // MMA N (multiple of 16, <= 128)
@@ -335,7 +336,8 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
         // tc_atb: this thread's share of the Y-tile transposition (loop invariant): chunk i covers
         // column nn = i % n_pad, K rows 4*cc .. 4*cc+3 with cc = i / n_pad
         constexpr int kYIter = (ATB && !PANEL) ? (NP * 8 + kTransformWarps * 32 - 1) / (kTransformWarps * 32) : 1;
-        int y_src[kYIter], y_dst[kYIter];
+        int y_src[kYIter], y_dst[kYIter], y_row[kYIter];
+        float y_mu[kYIter];
         if (ATB && !PANEL) {
 #pragma unroll
             for (int u = 0; u < kYIter; ++u) {
@@ -343,6 +345,8 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 const int nn = i % n_pad, cc = i / n_pad;
                 y_src[u] = (i < n_pad * 8) ? (cc * 4 * n_pad + nn) : -1;
                 y_dst[u] = nn * 128 + ((cc ^ (nn & 7)) << 4);
+                y_row[u] = cc * 4;
+                y_mu[u] = (p.mub_pad != nullptr && i < n_pad * 8) ? p.mub_pad[nn] : 0.f;
             }
         }
         Group g;
@@ -424,6 +428,14 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                         h.y = ys[n_pad];
                         h.z = ys[2 * n_pad];
                         h.w = ys[3 * n_pad];
+                        if (p.mub_pad != nullptr) {
+                            // centred Y: rows past n are TMA zero fill and must stay zero
+                            const int64_t r0 = g.row0 + kb * kKB + y_row[u];
+                            h.x = (r0 + 0 < p.n) ? h.x - y_mu[u] : 0.f;
+                            h.y = (r0 + 1 < p.n) ? h.y - y_mu[u] : 0.f;
+                            h.z = (r0 + 2 < p.n) ? h.z - y_mu[u] : 0.f;
+                            h.w = (r0 + 3 < p.n) ? h.w - y_mu[u] : 0.f;
+                        }
                         l4.x = h.x - __uint_as_float(__float_as_uint(h.x) & 0xFFFFE000u);
                         l4.y = h.y - __uint_as_float(__float_as_uint(h.y) & 0xFFFFE000u);
                         l4.z = h.z - __uint_as_float(__float_as_uint(h.z) & 0xFFFFE000u);
@@ -680,7 +692,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are TMA-loaded panels, or
                     // (row-major Y) produced by ALL transform warps - then both halves must have checked in first
                     if (!ATB || panel) mbar_wait(bar_full_b(bars, sb), phb);
-                    if (ATB && !panel) {
+                    // (tc_xb also checks both halves in first: measured faster than issuing per half there)
+                    constexpr bool kSplitIssue = ATB && panel;
+                    if (!kSplitIssue) {
                         mbar_wait(bar_a_ready(bars, (int)((2u * it) & (kASlots - 1))), ((2u * it) / kASlots) & 1u);
                         mbar_wait(bar_a_ready(bars, (int)((2u * it + 1u) & (kASlots - 1))), ((2u * it + 1u) / kASlots) & 1u);
                     }
@@ -696,7 +710,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t gran = 2u * it + (uint32_t)h;
                         const int ta = (int)(gran & (kASlots - 1));
-                        if (!ATB || panel) mbar_wait(bar_a_ready(bars, ta), (gran / kASlots) & 1u);
+                        if (kSplitIssue) mbar_wait(bar_a_ready(bars, ta), (gran / kASlots) & 1u);
                         tc_fence_after();
                         if (h == 0 && mt == 0 && lane == 0) trace_ev(p, 1, it);
                         const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kASlotCols + mt * 32);
@@ -889,7 +903,7 @@ inline bool atb_supported(const void* A, int64_t lda, int64_t da, const void* B,
 // b_panel: B is panel-major [ceil(n/32)][n_pad][32] (as written by launch_tc_xb with y_panel).
 inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t da, const float* mua, const float* B,
                           int64_t ldb, int64_t db, int64_t n, double* Z, int64_t ldz, bool b_panel = false,
-                          const float* B_lo_panel = nullptr) {
+                          const float* B_lo_panel = nullptr, const float* mub = nullptr) {
     const int n_pad = round_up(db, 16);
     int stages = 0, stages_b = 0;
     if (!pick_stages(true, n_pad, b_panel, stages, stages_b)) linalg_error("tc_atb: no pipeline configuration fits in shared memory");
@@ -907,6 +921,14 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     } else {
         p.map_bhi = make_map_2d(B, (uint64_t)db, (uint64_t)n, (uint64_t)ldb, (uint32_t)n_pad, 32, false);
         p.map_blo = p.map_bhi;
+    }
+    DBuf<float> mubp;
+    if (mub != nullptr) {
+        if (b_panel) linalg_error("tc_atb: panel-major Y cannot be centred on load");
+        mubp.alloc(ctx, (size_t)n_pad);
+        prep_mu_kernel<<<1, 256, 0, ctx->stream>>>(mub, db, n_pad, mubp.p);
+        check_launch(ctx);
+        p.mub_pad = mubp.p;
     }
     p.y_panel = b_panel ? 1 : 0;
     p.mu_pad = mup.p;
