@@ -53,6 +53,7 @@ struct IcaParams {
     int d, nc, fun;
     double* Ht;           // [d x nc] f64, accumulated
     double* gp;           // [nc] f64, accumulated
+    const double* state;  // optional: state[6] != 0 -> the fixed point has converged (or failed), do nothing
     long long* trace;     // optional clock64 timeline of CTA 0 (PETAL_ICA_TRACE)
 };
 
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
     const uint32_t bars = base + kOffBars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (p.n + kRows - 1) / kRows;
+    if (p.state != nullptr && p.state[6] != 0.0) return;  // on-device convergence flag (uniform over the grid)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kXStages; ++s) {
@@ -395,69 +397,86 @@ inline bool fused_supported(const void* X, int64_t ld, int64_t n, int64_t d, int
     return n >= 1024 && d >= 4 && d <= kD && nc >= 1 && nc <= kNC && (ld % 4 == 0) && is_aligned16(X) && n < ((int64_t)1 << 31);
 }
 
-// One fused pass: Ht[d x nc] += (X - mu)^T g((X - mu) Wt^T), gp[nc] += sum g'(.).  Wt is nc x d (f32, row-major).
-// Ht and gp must be zeroed by the caller.
-inline void launch_ica_fused(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, const float* mu,
-                             const float* Wt, int64_t nc, int fun, double* Ht, double* gp) {
-    DBuf<float> whi(ctx, (size_t)(kNC * kD)), wlo(ctx, (size_t)(kNC * kD)), mup(ctx, (size_t)kD);
-    // Bt[c][k] = Wt[c][k]  (operand tiles want [component][feature], K contiguous) -> "b_trans" view of an L x K matrix
-    prep_b_kernel<float><<<(unsigned)ceil_div((int64_t)kNC * kD, 256), 256, 0, ctx->stream>>>(Wt, d, 1, d, kD, (int)nc, kNC,
-                                                                                               whi.p, wlo.p);
-    check_launch(ctx);
-    prep_mu_kernel<<<1, 256, 0, ctx->stream>>>(mu, d, kD, mup.p);
-    check_launch(ctx);
+// Plan for the repeated fused pass of one FastICA fit: operand buffers and tensor maps are built once,
+// run() is a single kernel launch.  Ht[d x nc] += (X - mu)^T g((X - mu) W~^T), gp[nc] += sum g'(.); both must be
+// zero on entry (the update kernel re-zeroes them after consuming them).
+struct IcaFused {
+    DBuf<float> whi, wlo, mup;   // W~ hi / lo operand arrays [64][64] (zero padded), mu [64]
     IcaParams p;
-    std::memset(&p, 0, sizeof p);
-    p.map_x = make_map_2d(X, (uint64_t)d, (uint64_t)n, (uint64_t)ld, 32, kRows, true);
-    p.map_whi = make_map_2d(whi.p, kD, kNC, kD, 32, kNC, true);
-    p.map_wlo = make_map_2d(wlo.p, kD, kNC, kD, 32, kNC, true);
-    p.mu_pad = mup.p;
-    p.n = n;
-    p.d = (int)d;
-    p.nc = (int)nc;
-    p.fun = fun;
-    p.Ht = Ht;
-    p.gp = gp;
-    long long* trace = nullptr;
-    DBuf<long long> trbuf;
-    if (getenv("PETAL_ICA_TRACE")) {
-        trbuf.alloc(ctx, (size_t)kTraceEv * kTraceTiles);
-        trbuf.zero();
-        trace = trbuf.p;
-    }
-    p.trace = trace;
-    const int64_t ntiles = ceil_div(n, kRows);
-    const int grid = (int)std::min<int64_t>(ntiles, ctx->sm_count);
-    auto launch = [&](auto kernel) {
-        PETAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemIca));
-        KTimer kt(ctx, "ica_fused_f32", (double)n * d * sizeof(float));
-        kernel<<<grid, kThreadsIca, kSmemIca, ctx->stream>>>(p);
+    int grid = 0;
+    int fun = 0;
+    int64_t ntiles = 0;
+
+    void init(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, const float* mu, int64_t nc, int fun_,
+              double* Ht, double* gp, const double* state) {
+        whi.alloc(ctx, (size_t)(kNC * kD));
+        wlo.alloc(ctx, (size_t)(kNC * kD));
+        mup.alloc(ctx, (size_t)kD);
+        whi.zero();
+        wlo.zero();
+        prep_mu_kernel<<<1, 256, 0, ctx->stream>>>(mu, d, kD, mup.p);
         check_launch(ctx);
-    };
-    if (fun == PETAL_ICA_LOGCOSH) launch(ica_fused_kernel<PETAL_ICA_LOGCOSH>);
-    else if (fun == PETAL_ICA_EXP) launch(ica_fused_kernel<PETAL_ICA_EXP>);
-    else launch(ica_fused_kernel<PETAL_ICA_CUBE>);
-    if (trace) {
-        std::vector<long long> h((size_t)kTraceEv * kTraceTiles);
-        PETAL_CUDA(cudaMemcpyAsync(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
-        auto ev = [&](int e, int i) { return h[(size_t)e * kTraceTiles + i]; };
-        const int a = 8, b = (int)std::min<int64_t>(40, ceil_div(ntiles, grid) - 1);
-        if (b > a) {
-            auto mean = [&](int e1, int e0, int sh) {
-                double sacc = 0;
-                for (int i = a; i < b; ++i) sacc += (double)(ev(e1, i + sh) - ev(e0, i));
-                return sacc / (b - a);
-            };
-            fprintf(stderr,
-                    "[ica trace] period %.0f | row: xfull->a1 %.0f  a1->ufull %.0f  ufull->g %.0f  g->tilefree %.0f  tilefree->gready %.0f  "
-                    "gready->next xfull %.0f | feat: xfull->tilefree %.0f  tilefree->a2 %.0f | mma: a1got->m1 issued %.0f  m1->g/a2 got %.0f  "
-                    "->m2 issued %.0f  m2->next a1 got %.0f\n",
-                    mean(0, 0, 1), mean(1, 0, 0), mean(2, 1, 0), mean(3, 2, 0), mean(4, 3, 0), mean(5, 4, 0), mean(0, 5, 1),
-                    mean(7, 6, 0), mean(8, 7, 0), mean(10, 9, 0), mean(11, 10, 0), mean(12, 11, 0), mean(9, 12, 1));
+        std::memset(&p, 0, sizeof p);
+        p.map_x = make_map_2d(X, (uint64_t)d, (uint64_t)n, (uint64_t)ld, 32, kRows, true);
+        p.map_whi = make_map_2d(whi.p, kD, kNC, kD, 32, kNC, true);
+        p.map_wlo = make_map_2d(wlo.p, kD, kNC, kD, 32, kNC, true);
+        p.mu_pad = mup.p;
+        p.n = n;
+        p.d = (int)d;
+        p.nc = (int)nc;
+        p.fun = fun_;
+        p.Ht = Ht;
+        p.gp = gp;
+        p.state = state;
+        fun = fun_;
+        ntiles = ceil_div(n, kRows);
+        grid = (int)std::min<int64_t>(ntiles, ctx->sm_count);
+    }
+    // W~ (nc x d, f32 row-major) -> operand arrays (used when the update did not write them itself)
+    void set_w(petal_ctx* ctx, const float* Wt) {
+        prep_b_kernel<float><<<(unsigned)ceil_div((int64_t)kNC * kD, 256), 256, 0, ctx->stream>>>(Wt, p.d, 1, p.d, kD, p.nc, kNC,
+                                                                                                  whi.p, wlo.p);
+        check_launch(ctx);
+    }
+    void run(petal_ctx* ctx) {
+        DBuf<long long> trbuf;
+        IcaParams q = p;
+        if (getenv("PETAL_ICA_TRACE")) {
+            trbuf.alloc(ctx, (size_t)kTraceEv * kTraceTiles);
+            trbuf.zero();
+            q.trace = trbuf.p;
+        }
+        auto launch = [&](auto kernel) {
+            PETAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemIca));
+            KTimer kt(ctx, "ica_fused_f32", (double)p.n * p.d * sizeof(float));
+            kernel<<<grid, kThreadsIca, kSmemIca, ctx->stream>>>(q);
+            check_launch(ctx);
+        };
+        if (fun == PETAL_ICA_LOGCOSH) launch(ica_fused_kernel<PETAL_ICA_LOGCOSH>);
+        else if (fun == PETAL_ICA_EXP) launch(ica_fused_kernel<PETAL_ICA_EXP>);
+        else launch(ica_fused_kernel<PETAL_ICA_CUBE>);
+        if (q.trace) {
+            std::vector<long long> h((size_t)kTraceEv * kTraceTiles);
+            PETAL_CUDA(cudaMemcpyAsync(h.data(), q.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            auto ev = [&](int e, int i) { return h[(size_t)e * kTraceTiles + i]; };
+            const int a = 8, b = (int)std::min<int64_t>(40, ceil_div(ntiles, grid) - 1);
+            if (b > a) {
+                auto mean = [&](int e1, int e0, int sh) {
+                    double sacc = 0;
+                    for (int i = a; i < b; ++i) sacc += (double)(ev(e1, i + sh) - ev(e0, i));
+                    return sacc / (b - a);
+                };
+                fprintf(stderr,
+                        "[ica trace] period %.0f | row: xfull->a1 %.0f  a1->ufull %.0f  ufull->g %.0f  g->tilefree %.0f  tilefree->gready %.0f  "
+                        "gready->next xfull %.0f | feat: xfull->tilefree %.0f  tilefree->a2 %.0f | mma: a1got->m1 issued %.0f  m1->g/a2 got %.0f  "
+                        "->m2 issued %.0f  m2->next a1 got %.0f\n",
+                        mean(0, 0, 1), mean(1, 0, 0), mean(2, 1, 0), mean(3, 2, 0), mean(4, 3, 0), mean(5, 4, 0), mean(0, 5, 1),
+                        mean(7, 6, 0), mean(8, 7, 0), mean(10, 9, 0), mean(11, 10, 0), mean(12, 11, 0), mean(9, 12, 1));
+            }
         }
     }
-}
+};
 
 }  // namespace ica
 }  // namespace petal

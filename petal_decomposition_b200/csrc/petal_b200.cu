@@ -689,7 +689,12 @@ template <typename T>
 __global__ void __launch_bounds__(kIcaThreads)
 ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __restrict__ gp, double* __restrict__ W,
                   const double* __restrict__ K1 /* nc x d or null */, int nc, int d, double inv_n, int lim_variant,
-                  T* __restrict__ Wt_out /* nc x d */, double* __restrict__ out2 /* [lim, status] */) {
+                  T* __restrict__ Wt_out /* nc x d */, double* __restrict__ out2 /* state, see below */, double tol,
+                  float* __restrict__ whi, float* __restrict__ wlo /* [64][64] operand arrays of the one-pass kernel or null */,
+                  double* __restrict__ consumed, int consumed_n /* zeroed after a successful update (Ht | gp) */) {
+    // state: [0] lim, [1] 1 = Newton-Schulz failed, [2] NS steps, [3..5] cycle counters, [6] done (1 converged,
+    // 2 failed: the host redoes this iteration with the Jacobi path), [7] completed fixed-point iterations
+    if (out2[6] != 0.0) return;
     extern __shared__ double sm[];
     const int ld = nc + 1;
     double* X = sm;
@@ -745,20 +750,30 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
         for (int e = tid; e < nc * nc; e += kIcaThreads) X[(e / nc) * ld + e % nc] *= inv;
     }
     __syncthreads();
-    // Newton-Schulz
+    // Newton-Schulz with the optimal per-step scaling for singular values in [l, 1]:
+    //   X <- X (1.5 a I - 0.5 a^3 X^T X),  a^2 = 3 / (1 + l + l^2),  l <- 1.5 a l - 0.5 (a l)^3
+    // (a = 1 is the plain iteration; a -> sqrt(3) while l is small grows the small singular values 2.6x per
+    // step instead of 1.5x).  l is only a guess of the smallest singular value: values below it still grow by
+    // >= 1.5x per step, and once l reaches 1 the iteration is the unscaled, quadratically convergent one.
+    // l0 = 1e-3: the 1-norm/inf-norm scaling above over-estimates |Gd|_2 by ~5x for the Gd of a FastICA run, whose
+    // own conditioning is 1e-2 .. 0.7, so the scaled singular values start at 1e-3 .. 0.1 (12 steps instead of 20).
     bool converged = false;
     int ns_it = 0;
+    double lo = 1e-3;
     for (int it = 0; ok && it < 100; ++it) {
         ns_it = it;
         smem_gemm<true>(X, X, Tm, nc, ld);  // T = X^T X
         __syncthreads();
+        const double alpha = (lo < 1.0 - 1e-9) ? sqrt(3.0 / (1.0 + lo + lo * lo)) : 1.0;
+        const double alpha3 = alpha * alpha * alpha;
+        lo = fmin(1.0, 1.5 * alpha * lo - 0.5 * alpha3 * lo * lo * lo);
         double err = 0.0;
         for (int e = tid; e < nc * nc; e += kIcaThreads) {
             const int i = e / nc, j = e % nc;
             const double t = Tm[i * ld + j];
             const double dlt = t - (i == j ? 1.0 : 0.0);
             err += dlt * dlt;
-            Tm[i * ld + j] = (i == j ? 1.5 : 0.0) - 0.5 * t;
+            Tm[i * ld + j] = (i == j ? 1.5 * alpha : 0.0) - 0.5 * alpha3 * t;
         }
         err = block_reduce_sum(err, red);
         if (!(err == err)) {
@@ -769,7 +784,7 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
             converged = true;
             break;
         }
-        smem_gemm<false>(X, Tm, Y, nc, ld);  // Y = X (1.5 I - 0.5 T)
+        smem_gemm<false>(X, Tm, Y, nc, ld);  // Y = X (1.5 a I - 0.5 a^3 T)
         __syncthreads();
         double* t = X;
         X = Y;
@@ -779,6 +794,7 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
         if (tid == 0) {
             out2[0] = 0.0;
             out2[1] = 1.0;
+            out2[6] = 2.0;
         }
         return;
     }
@@ -818,12 +834,34 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
             for (int u = 0; u < 4; ++u)
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
-                    if (ty + 16 * u < nc && tx + 16 * v < d) Wt_out[(size_t)(ty + 16 * u) * d + tx + 16 * v] = (T)acc[u][v];
+                    if (ty + 16 * u < nc && tx + 16 * v < d) {
+                        const int c = ty + 16 * u, k = tx + 16 * v;
+                        Wt_out[(size_t)c * d + k] = (T)acc[u][v];
+                        if (whi != nullptr) {
+                            const float hf = __uint_as_float(__float_as_uint((float)acc[u][v]) & 0xFFFFE000u);
+                            whi[c * 64 + k] = hf;
+                            wlo[c * 64 + k] = (float)(acc[u][v] - (double)hf);
+                        }
+                    }
         }
     } else {
-        for (int e = tid; e < nc * d; e += kIcaThreads) Wt_out[e] = (T)X[(e / d) * ld + e % d];
+        for (int e = tid; e < nc * d; e += kIcaThreads) {
+            const double w = X[(e / d) * ld + e % d];
+            Wt_out[e] = (T)w;
+            if (whi != nullptr) {
+                const float hf = __uint_as_float(__float_as_uint((float)w) & 0xFFFFE000u);
+                whi[(e / d) * 64 + e % d] = hf;
+                wlo[(e / d) * 64 + e % d] = (float)(w - (double)hf);
+            }
+        }
     }
+    if (consumed != nullptr)
+        for (int e = tid; e < consumed_n; e += kIcaThreads) consumed[e] = 0.0;
     if (tid == 0) {
+        if (Ht != nullptr) {
+            out2[7] += 1.0;
+            if (best < tol) out2[6] = 1.0;
+        }
         out2[0] = best;
         out2[1] = 0.0;
         out2[2] = (double)ns_it;
@@ -841,14 +879,30 @@ bool ica_one_pass_supported<float>(petal_ctx* ctx, const float* X, int64_t ld, i
     if (const char* e = getenv("PETAL_ICA_ONEPASS")) if (e[0] == '0') return false;
     return ctx->f32_engine == 1 && ica::fused_supported(X, ld, n, d, nc);
 }
-inline void ica_one_pass(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, const float* mu, const float* Wt,
-                         int64_t nc, int fun, double* Ht, double* gp) {
-    ica::launch_ica_fused(ctx, X, ld, n, d, mu, Wt, nc, fun, Ht, gp);
-}
-inline void ica_one_pass(petal_ctx*, const double*, int64_t, int64_t, int64_t, const double*, const double*, int64_t, int,
-                         double*, double*) {
-    linalg_error("one-pass FastICA kernel is f32 only");
-}
+template <typename T>
+struct IcaOnePass {  // f64: never selected
+    void init(petal_ctx*, const T*, int64_t, int64_t, int64_t, const T*, int64_t, int, double*, double*, const double*) {
+        linalg_error("one-pass FastICA kernel is f32 only");
+    }
+    void set_w(petal_ctx*, const T*) {}
+    void run(petal_ctx*) {}
+    float* whi_ptr() { return nullptr; }
+    float* wlo_ptr() { return nullptr; }
+};
+template <>
+struct IcaOnePass<float> {
+    ica::IcaFused f;
+    bool on = false;
+    void init(petal_ctx* ctx, const float* X, int64_t ld, int64_t n, int64_t d, const float* mu, int64_t nc, int fun, double* Ht,
+              double* gp, const double* state) {
+        f.init(ctx, X, ld, n, d, mu, nc, fun, Ht, gp, state);
+        on = true;
+    }
+    void set_w(petal_ctx* ctx, const float* Wt) { f.set_w(ctx, Wt); }
+    void run(petal_ctx* ctx) { f.run(ctx); }
+    float* whi_ptr() { return on ? f.whi.p : nullptr; }
+    float* wlo_ptr() { return on ? f.wlo.p : nullptr; }
+};
 
 // ica_par (reference src/ica.rs:319-361) on data X[n x d] with whitening folded in:
 // the whitened sample is x1 = K1 (x - mu) with K1 = sqrt(n) K (nc x d); K1 == nullptr means the
@@ -865,11 +919,15 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
     double* H = Hg.p;
     double* Ht = Htg.p;          // [H^T (d x nc) | sum g' (nc)] reduced across ranks together
     double* gp = Htg.p + nc * d;
+    const int htg_n = (int)(nc * d + nc);
     const double inv_n = 1.0 / (double)n_total;
     int64_t iters = max_iter;
     double lim = 0.0;
     const bool fused = (nc <= kIcaFusedMax) && (d <= kIcaFusedMax);
-    DBuf<double> out2(ctx, 8);
+    DBuf<double> state(ctx, 8);
+    state.zero();
+    Htg.zero();
+    const size_t upd_smem = 3 * (size_t)nc * (nc + 1) * sizeof(double);
     if (fused) {
         static bool attr_set = false;
         if (!attr_set) {
@@ -878,6 +936,8 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
             attr_set = true;
         }
     }
+    IcaOnePass<T> pass;
+    if (one_pass) pass.init(ctx, X, d, n, d, mu, nc, fun, Ht, gp, state.p);
     auto make_wt = [&]() {
         // W~ = W K1 so that W x1 = W~ (x - mu): the whitened copy is never materialised
         const double* Wfull = W;
@@ -886,31 +946,38 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
             Wfull = Wk.p;
         }
         launch_cast<double, T>(ctx, Wfull, Wt.p, nc * d);
+        if (one_pass) pass.set_w(ctx, Wt.p);
+    };
+    auto read_state = [&](double* h) {
+        PETAL_CUDA(cudaMemcpyAsync(h, state.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    };
+    auto launch_update = [&](bool init) {
+        KTimer kt(ctx, "ica_update", 0.0);
+        ica_update_kernel<T><<<1, kIcaThreads, upd_smem, ctx->stream>>>(init ? nullptr : Ht, init ? nullptr : gp, W, K1, (int)nc,
+                                                                       (int)d, inv_n, lim_variant, Wt.p, state.p, tol,
+                                                                       pass.whi_ptr(), pass.wlo_ptr(), init ? nullptr : Htg.p, htg_n);
+        launch1(ctx);
     };
     // W = symmetric_decorrelation(w_init) (src/ica.rs:329) and the first W~
     bool init_done = false;
+    double hs[8];
     if (fused) {
         PETAL_CUDA(cudaMemcpyAsync(W, w_init, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        {
-            KTimer kt(ctx, "ica_update", 0.0);
-            ica_update_kernel<T><<<1, kIcaThreads, 3 * (size_t)nc * (nc + 1) * sizeof(double), ctx->stream>>>(
-                nullptr, nullptr, W, K1, (int)nc, (int)d, inv_n, lim_variant, Wt.p, out2.p);
-            launch1(ctx);
-        }
-        double h2[2] = {0.0, 1.0};
-        PETAL_CUDA(cudaMemcpyAsync(h2, out2.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
-        init_done = (h2[1] == 0.0);
+        launch_update(true);
+        read_state(hs);
+        init_done = (hs[6] == 0.0);
+        if (!init_done) state.zero();
     }
     if (!init_done) {
         symmetric_decorrelation(ctx, w_init, nc, W);
         make_wt();
     }
-    for (int64_t it = 0; it < max_iter; ++it) {
+    // streaming half of one fixed-point iteration: Ht, gp (summed over ranks)
+    auto stream_pass = [&]() {
         if (one_pass) {
             // U, g(U), sum g'(U) and H^T in a single pass over X (tcgen05; U and g(U) never reach HBM)
-            PETAL_CUDA(cudaMemsetAsync(Htg.p, 0, (size_t)(nc * d + nc) * sizeof(double), ctx->stream));
-            ica_one_pass(ctx, X, d, n, d, mu, Wt.p, nc, fun, Ht, gp);
+            pass.run(ctx);
         } else {
             // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
             gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
@@ -921,43 +988,69 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
             // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
             gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht);
         }
-        allreduce_sum(ctx, Htg.p, (size_t)(nc * d + nc));
-        bool done_small = false;
-        if (fused) {
-            KTimer kt(ctx, "ica_update", 0.0);
-            ica_update_kernel<T><<<1, kIcaThreads, 3 * (size_t)nc * (nc + 1) * sizeof(double), ctx->stream>>>(
-                Ht, gp, W, K1, (int)nc, (int)d, inv_n, lim_variant, Wt.p, out2.p);
-            launch1(ctx);
-            double h2[8] = {0.0, 1.0};
-            PETAL_CUDA(cudaMemcpyAsync(h2, out2.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (getenv("PETAL_PHASES")) fprintf(stderr, "[ica_update] it %lld lim %.3e ns_iters %.0f cycles: setup %.0f ns %.0f tail %.0f\n", (long long)it, h2[0], h2[2], h2[3], h2[4], h2[5]);
-            if (h2[1] == 0.0) {
-                lim = h2[0];
-                done_small = true;
-            }
+        allreduce_sum(ctx, Htg.p, (size_t)htg_n);
+    };
+    // small half on the Jacobi path (any nc; also the fallback when Newton-Schulz hits a singular Gd)
+    auto slow_update = [&]() {
+        launch_transpose(ctx, Ht, d, nc, H);
+        // Gd = (H K1^T) / n - diag(mean g') W   (src/ica.rs:334-342)
+        const double* HKp = H;
+        if (K1) {
+            gemm_xb<double>(ctx, H, d, nc, d, K1, d, true, nc, nullptr, nullptr, HK.p, nc);
+            HKp = HK.p;
         }
-        if (!done_small) {
-            launch_transpose(ctx, Ht, d, nc, H);
-            // Gd = (H K1^T) / n - diag(mean g') W   (src/ica.rs:334-342)
-            const double* HKp = H;
-            if (K1) {
-                gemm_xb<double>(ctx, H, d, nc, d, K1, d, true, nc, nullptr, nullptr, HK.p, nc);
-                HKp = HK.p;
+        ica_gd_kernel<<<(unsigned)ceil_div(nc * nc, 256), 256, 0, ctx->stream>>>(HKp, gp, W, nc, inv_n, Gd.p);
+        launch1(ctx);
+        symmetric_decorrelation(ctx, Gd.p, nc, W1.p);  // src/ica.rs:343
+        ica_lim_kernel<<<1, 256, 0, ctx->stream>>>(W1.p, W, (int)nc, lim_variant, limd.p);
+        launch1(ctx);
+        PETAL_CUDA(cudaMemcpyAsync(W, W1.p, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        PETAL_CUDA(cudaMemcpyAsync(&lim, limd.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        make_wt();
+        Htg.zero();
+    };
+    // The convergence test (src/ica.rs:344-357) runs on the device: the update kernel raises state[6] when
+    // lim < tol and every later launch of the batch returns at once, so the host only looks every `batch` iterations.
+    const int64_t batch = (fused && one_pass) ? 4 : 1;
+    int64_t it = 0;
+    while (it < max_iter) {
+        if (!fused) {
+            stream_pass();
+            slow_update();
+            ++it;
+            if (lim < tol) {  // src/ica.rs:355-357
+                iters = it;
+                break;
             }
-            ica_gd_kernel<<<(unsigned)ceil_div(nc * nc, 256), 256, 0, ctx->stream>>>(HKp, gp, W, nc, inv_n, Gd.p);
-            launch1(ctx);
-            symmetric_decorrelation(ctx, Gd.p, nc, W1.p);  // src/ica.rs:343
-            ica_lim_kernel<<<1, 256, 0, ctx->stream>>>(W1.p, W, (int)nc, lim_variant, limd.p);
-            launch1(ctx);
-            PETAL_CUDA(cudaMemcpyAsync(W, W1.p, (size_t)(nc * nc) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            PETAL_CUDA(cudaMemcpyAsync(&lim, limd.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
-            make_wt();
+            continue;
         }
-        if (lim < tol) {  // src/ica.rs:355-357
-            iters = it + 1;
+        const int64_t b = std::min<int64_t>(batch, max_iter - it);
+        for (int64_t j = 0; j < b; ++j) {
+            stream_pass();
+            launch_update(false);
+        }
+        read_state(hs);
+        if (getenv("PETAL_PHASES"))
+            fprintf(stderr, "[ica_update] iters %.0f done %.0f lim %.3e ns_steps %.0f cycles: setup %.0f ns %.0f tail %.0f\n", hs[7],
+                    hs[6], hs[0], hs[2], hs[3], hs[4], hs[5]);
+        it = (int64_t)hs[7];
+        lim = hs[0];
+        if (hs[6] == 1.0) {
+            iters = it;
             break;
+        }
+        if (hs[6] == 2.0) {
+            // singular Gd: redo this iteration's small half with the Jacobi path (Ht / gp are still intact)
+            slow_update();
+            ++it;
+            const double st[2] = {lim < tol ? 1.0 : 0.0, (double)it};
+            PETAL_CUDA(cudaMemcpyAsync(state.p + 6, st, 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (lim < tol) {
+                iters = it;
+                break;
+            }
         }
     }
     *n_iter_out = iters;
