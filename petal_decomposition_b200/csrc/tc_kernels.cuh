@@ -33,9 +33,11 @@ constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
 constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
 constexpr int kTmemCols = 512;
 constexpr int kYBufs = 3;         // tc_atb: ring of transposed Y tiles (decoupled from the 2 TMEM operand stages)
-constexpr int kASlots = 4;                 // TMEM operand ring: one slot per half K block (16 k-values)
+constexpr int kASlotsMax = 4;              // TMEM operand ring: one slot per half K block (16 k-values); 3 or 4 slots
 constexpr int kASlotCols = kMT * 32;       // per slot: MT x (16 hi + 16 lo) columns
-constexpr int kAccBase = kASlots * kASlotCols;  // accumulators start after the operand ring (256)
+// accumulators start after the operand ring: 4 slots -> column 256, one accumulator set (MT x n_pad columns);
+// 3 slots -> column 192, two sets (tc_xb with n_pad <= 80): the next super-tile's MMAs run while the previous
+// accumulators are drained
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -187,6 +189,9 @@ struct TcParams {
     int L;                // valid output columns
     int stages;           // X ring depth (X tile + mu slice; released as soon as the transform has read it)
     int stages_b;         // B ring depth (B / Y tiles; released by the MMAs, or by the transform for row-major Y)
+    int a_slots;          // TMEM operand ring slots (3 or 4)
+    int acc_bufs;         // accumulator sets in TMEM (1 or 2)
+    int acc_base;         // first accumulator column (a_slots * 64)
     // tc_xb outputs
     float* Y;
     float* Ylo;           // tc_xb panel mode: second panel with y - tf32(y) (the B_lo operand of a later tc_atb)
@@ -253,8 +258,8 @@ __device__ __forceinline__ uint32_t bar_full_b(uint32_t base, int s) { return ba
 __device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (24 + (uint32_t)s); }
 __device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }  // 4 slots
 __device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (36 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base) { return base + 8u * 40; }
-__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base) { return base + 8u * 41; }
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, int b) { return base + 8u * (40 + 2 * (uint32_t)b); }   // 40, 42
+__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base, int b) { return base + 8u * (41 + 2 * (uint32_t)b); }  // 41, 43
 __device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (44 + (uint32_t)t); }
 
 // ------------------------------------------------------------------------------------------
@@ -349,6 +354,93 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 y_mu[u] = (p.mub_pad != nullptr && i < n_pad * 8) ? p.mub_pad[nn] : 0.f;
             }
         }
+        // ---- tc_xb epilogue, drained one 16-column chunk at a time.  With two accumulator sets the drain of
+        // super-tile g is deferred into the K loop of super-tile g+1 (one chunk after each of its first K blocks),
+        // so the tensor pipe keeps running while Y is written.
+        const int acc_bufs = p.acc_bufs;
+        const int xb_chunks = ATB ? 0 : (panel ? (n_pad - half * 16 + 31) / 32 : n_pad / 16);
+        bool pend_on = false;
+        int64_t pend_row0 = 0;
+        uint32_t pend_gi = 0;
+        int pend_next = 0;
+        auto xb_drain_chunk = [&](int64_t row0, int buf, int j) {
+            const uint32_t acc_col = (uint32_t)(p.acc_base + buf * kMT * n_pad + mt * n_pad);
+            if (panel) {
+                // panel-major Y [row block of 32][n_pad][32]: lane = row inside the block, so for each
+                // column the warp writes one full 128 B line.  The two warps of a lane-quarter pair
+                // take alternate 16-column chunks.  Rows past n are written as zeros.
+                const int c0 = half * 16 + 32 * j;
+                const int64_t r = row0 + mt * 128 + lrow;
+                const int64_t rblk = (row0 + mt * 128 + q * 32) >> 5;
+                float* yb = p.Y + (rblk * n_pad) * 32 + lane;
+                float* yl = p.Ylo + (rblk * n_pad) * 32 + lane;
+                const bool valid = r < p.n;
+                const bool blk_valid = rblk * 32 < p.n;  // the panel buffer ends at the last partial row block
+                uint32_t w[16];
+                tmem_ld16(tmem_base + lane_field + acc_col + (uint32_t)c0, w);
+                tmem_ld_wait();
+                if (blk_valid) {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const float y = valid ? __uint_as_float(w[jj]) : 0.f;
+                        yb[(c0 + jj) * 32] = y;
+                        yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
+                    }
+                }
+            } else {
+                // Each warp of a lane-quarter pair drains 16 of the 32 lanes with the 16x256b pattern:
+                // four lanes hold 8 consecutive columns of one row, so every store instruction writes
+                // whole 32 B sectors (8 rows x 32 B).
+                const int c0 = 16 * j;
+                const int t0 = lane & 3, t1 = lane >> 2;
+                const uint32_t acc16 = tmem_base + ((uint32_t)(q * 32 + half * 16) << 16) + acc_col;
+                const int64_t ra = row0 + mt * 128 + q * 32 + half * 16 + t1;
+                const int64_t rb = ra + 8;
+                uint32_t w[8];
+                tmem_ld_16x256b_x2(acc16 + (uint32_t)c0, w);
+                tmem_ld_wait();
+                const int ca = c0 + 2 * t0, cb = ca + 8;
+                if (p.y_vec) {
+                    if (ra < p.n) {
+                        if (ca + 1 < p.ldy)
+                            *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) =
+                                make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
+                        if (cb + 1 < p.ldy)
+                            *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) =
+                                make_float2(__uint_as_float(w[4]), __uint_as_float(w[5]));
+                    }
+                    if (rb < p.n) {
+                        if (ca + 1 < p.ldy)
+                            *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) =
+                                make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
+                        if (cb + 1 < p.ldy)
+                            *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) =
+                                make_float2(__uint_as_float(w[6]), __uint_as_float(w[7]));
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int64_t r = (e & 2) ? rb : ra;
+                        const int c = ((e & 4) ? cb : ca) + (e & 1);
+                        if (r < p.n && c < p.ldy) p.Y[r * p.ldy + c] = __uint_as_float(w[e]);
+                    }
+                }
+            }
+        };
+        auto xb_drain_step = [&]() {
+            const int buf = (acc_bufs == 2) ? (int)(pend_gi & 1u) : 0;
+            if (pend_next == 0) {
+                mbar_wait(bar_acc_full(bars, buf), (acc_bufs == 2) ? ((pend_gi >> 1) & 1u) : (pend_gi & 1u));
+                tc_fence_after();
+            }
+            if (pend_next < xb_chunks) xb_drain_chunk(pend_row0, buf, pend_next);
+            if (++pend_next >= xb_chunks) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty(bars, buf));
+                pend_on = false;
+            }
+        };
         Group g;
         g.f0 = 0;
         for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
@@ -360,8 +452,8 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 const int s = (int)(it % (uint32_t)S);
                 const uint32_t ph = (it / (uint32_t)S) & 1u;
                 const uint32_t gran = 2u * it + (uint32_t)half;  // this warp's half K block
-                const int ta = (int)(gran & (kASlots - 1));
-                const uint32_t pa = (gran / kASlots) & 1u;
+                const int ta = (int)(gran % (uint32_t)p.a_slots);
+                const uint32_t pa = (gran / (uint32_t)p.a_slots) & 1u;
                 mbar_wait(bar_full(bars, s), ph);
                 if (warp == 0 && lane == 0) trace_ev(p, 3, it);
                 uint32_t v[16];
@@ -466,96 +558,41 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_a_ready(bars, ta));
                 if (warp == 0 && lane == 0) trace_ev(p, 6, it);
+                if (!ATB && pend_on && kb >= 1) xb_drain_step();  // previous super-tile, one chunk per K block
             }
             if (!ATB && row_valid) ss += (double)((ss0 + ss1) + (ss2 + ss3));
 
             // ---------------- epilogue for this group ----------------
-            if constexpr (epi) {
-                mbar_wait(bar_acc_full(bars), (uint32_t)gi & 1u);
+            if constexpr (ATB) {
+                mbar_wait(bar_acc_full(bars, 0), (uint32_t)gi & 1u);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad);
-                if constexpr (ATB) {
+                const uint32_t acc = tmem_base + lane_field + (uint32_t)(p.acc_base + mt * n_pad);
 #pragma unroll
-                    for (int ch = 0; ch < kAccChunks; ++ch) {
-                        const int c0 = (2 * ch + half) * 16;
-                        if (c0 < NP) {
-                            uint32_t w[16];
-                            tmem_ld16(acc + (uint32_t)c0, w);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) racc[ch * 16 + j] += __uint_as_float(w[j]);
-                        }
-                    }
-                } else if constexpr (!ATB) {
-                    if (panel) {
-                        // panel-major Y [row block of 32][n_pad][32]: lane = row inside the block, so for each
-                        // column the warp writes one full 128 B line.  The two warps of a lane-quarter pair
-                        // take alternate 16-column chunks.  Rows past n are written as zeros.
-                        const int64_t r = g.row0 + mt * 128 + lrow;
-                        const int64_t rblk = (g.row0 + mt * 128 + q * 32) >> 5;
-                        float* yb = p.Y + (rblk * n_pad) * 32 + lane;
-                        float* yl = p.Ylo + (rblk * n_pad) * 32 + lane;
-                        const bool valid = r < p.n;
-                        const bool blk_valid = rblk * 32 < p.n;  // the panel buffer ends at the last partial row block
-                        for (int c0 = half * 16; c0 < n_pad; c0 += 32) {
-                            uint32_t w[16];
-                            tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccBase + mt * n_pad + c0), w);
-                            tmem_ld_wait();
-                            if (!blk_valid) continue;
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float y = valid ? __uint_as_float(w[j]) : 0.f;
-                                yb[(c0 + j) * 32] = y;
-                                yl[(c0 + j) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
-                            }
-                        }
-                    } else {
-                    // Each warp of a lane-quarter pair drains 16 of the 32 lanes with the 16x256b pattern:
-                    // four lanes hold 8 consecutive columns of one row, so every store instruction writes
-                    // whole 32 B sectors (8 rows x 32 B).
-                    const int t0 = lane & 3, t1 = lane >> 2;
-                    const uint32_t acc16 = tmem_base + ((uint32_t)(q * 32 + half * 16) << 16) +
-                                           (uint32_t)(kAccBase + mt * n_pad);
-                    const int64_t ra = g.row0 + mt * 128 + q * 32 + half * 16 + t1;
-                    const int64_t rb = ra + 8;
-                    for (int c0 = 0; c0 < n_pad; c0 += 16) {
-                        uint32_t w[8];
-                        tmem_ld_16x256b_x2(acc16 + (uint32_t)c0, w);
+                for (int ch = 0; ch < kAccChunks; ++ch) {
+                    const int c0 = (2 * ch + half) * 16;
+                    if (c0 < NP) {
+                        uint32_t w[16];
+                        tmem_ld16(acc + (uint32_t)c0, w);
                         tmem_ld_wait();
-                        const int ca = c0 + 2 * t0, cb = ca + 8;
-                        if (p.y_vec) {
-                            if (ra < p.n) {
-                                if (ca + 1 < p.ldy)
-                                    *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) =
-                                        make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
-                                if (cb + 1 < p.ldy)
-                                    *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) =
-                                        make_float2(__uint_as_float(w[4]), __uint_as_float(w[5]));
-                            }
-                            if (rb < p.n) {
-                                if (ca + 1 < p.ldy)
-                                    *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) =
-                                        make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
-                                if (cb + 1 < p.ldy)
-                                    *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) =
-                                        make_float2(__uint_as_float(w[6]), __uint_as_float(w[7]));
-                            }
-                        } else {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int64_t r = (e & 2) ? rb : ra;
-                                const int c = ((e & 4) ? cb : ca) + (e & 1);
-                                if (r < p.n && c < p.ldy) p.Y[r * p.ldy + c] = __uint_as_float(w[e]);
-                            }
-                        }
-                    }
+                        for (int j = 0; j < 16; ++j) racc[ch * 16 + j] += __uint_as_float(w[j]);
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty(bars));
+                if (lane == 0) mbar_arrive(bar_acc_empty(bars, 0));
+            } else {
+                while (pend_on) xb_drain_step();  // whatever is left of the previous super-tile
+                pend_on = true;
+                pend_row0 = g.row0;
+                pend_gi = (uint32_t)gi;
+                pend_next = 0;
+                if (acc_bufs != 2)
+                    while (pend_on) xb_drain_step();  // single accumulator set: drain now
             }
         }
+        if (!ATB)
+            while (pend_on) xb_drain_step();
         if constexpr (ATB) {
             // the CTA's partial (256 features x L) -> global f64 accumulator
             const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
@@ -598,13 +635,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             // released by the two MMA warps, or by the transform warps when they consume the raw row-major Y tile
             mbar_init(bar_empty_b(bars, s), (ATB && !panel) ? kTransformWarps : kMT);
         }
-        for (int t = 0; t < kASlots; ++t) {
+        for (int t = 0; t < kASlotsMax; ++t) {
             mbar_init(bar_a_ready(bars, t), kTransformWarps / 2);  // the 8 warps that own this half of a K block
             mbar_init(bar_a_free(bars, t), kMT);
         }
-        mbar_init(bar_acc_full(bars), kMT);
+        mbar_init(bar_acc_full(bars, 0), kMT);
+        mbar_init(bar_acc_full(bars, 1), kMT);
         for (int t = 0; t < kYBufs; ++t) mbar_init(bar_y_free(bars, t), kMT);
-        mbar_init(bar_acc_empty(bars), kTransformWarps);
+        mbar_init(bar_acc_empty(bars, 0), kTransformWarps);
+        mbar_init(bar_acc_empty(bars, 1), kTransformWarps);
         fence_barrier_init();
     }
     if (warp == kTransformWarps + 3) tmem_alloc(base + L.tmem_slot, kTmemCols);
@@ -680,11 +719,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             // every address / descriptor is warp-uniform; only the tcgen05 instructions are elected.
             const int mt = warp - (kTransformWarps + 1);
             const uint32_t idesc = make_idesc_tf32(n_pad, 0);
-            const uint32_t acc = tmem_base + (uint32_t)(kAccBase + mt * n_pad);
+            const uint32_t aslots = (uint32_t)p.a_slots;
             uint32_t it = 0;
             Group g;
             for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
-                mbar_wait(bar_acc_empty(bars), ((uint32_t)gi & 1u) ^ 1u);
+                const int abuf = (p.acc_bufs == 2) ? (int)(gi & 1) : 0;
+                const uint32_t acc = tmem_base + (uint32_t)(p.acc_base + abuf * kMT * n_pad + mt * n_pad);
+                mbar_wait(bar_acc_empty(bars, abuf), ((p.acc_bufs == 2) ? ((uint32_t)(gi >> 1) & 1u) : ((uint32_t)gi & 1u)) ^ 1u);
                 tc_fence_after();
                 for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
                     const int sb = (int)(it % (uint32_t)SB);
@@ -695,8 +736,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     // (tc_xb also checks both halves in first: measured faster than issuing per half there)
                     constexpr bool kSplitIssue = ATB && panel;
                     if (!kSplitIssue) {
-                        mbar_wait(bar_a_ready(bars, (int)((2u * it) & (kASlots - 1))), ((2u * it) / kASlots) & 1u);
-                        mbar_wait(bar_a_ready(bars, (int)((2u * it + 1u) & (kASlots - 1))), ((2u * it + 1u) / kASlots) & 1u);
+                        mbar_wait(bar_a_ready(bars, (int)((2u * it) % aslots)), ((2u * it) / aslots) & 1u);
+                        mbar_wait(bar_a_ready(bars, (int)((2u * it + 1u) % aslots)), ((2u * it + 1u) / aslots) & 1u);
                     }
                     // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
                     const int yb = (int)(it % (uint32_t)kYBufs);
@@ -709,8 +750,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t gran = 2u * it + (uint32_t)h;
-                        const int ta = (int)(gran & (kASlots - 1));
-                        if (kSplitIssue) mbar_wait(bar_a_ready(bars, ta), (gran / kASlots) & 1u);
+                        const int ta = (int)(gran % aslots);
+                        if (kSplitIssue) mbar_wait(bar_a_ready(bars, ta), (gran / aslots) & 1u);
                         tc_fence_after();
                         if (h == 0 && mt == 0 && lane == 0) trace_ev(p, 1, it);
                         const uint32_t a_hi0 = tmem_base + (uint32_t)(ta * kASlotCols + mt * 32);
@@ -738,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     __syncwarp();
                     if (mt == 0 && lane == 0) trace_ev(p, 2, it);
                 }
-                if (elect_one()) tc_commit(bar_acc_full(bars));
+                if (elect_one()) tc_commit(bar_acc_full(bars, abuf));
                 __syncwarp();
             }
         }
@@ -886,6 +927,12 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     p.y_panel = y_panel ? 1 : 0;
     p.Ylo = Y_lo_panel;
     p.sumsq = sumsq;
+    // two accumulator sets (deferred epilogue) whenever they fit beside a 3-slot operand ring: 192 + 4 n_pad <= 512
+    const char* dbe = getenv("PETAL_XB_DBUF");
+    const bool dbuf = (n_pad <= 80) && !(dbe && dbe[0] == '0');
+    p.a_slots = dbuf ? 3 : 4;
+    p.acc_bufs = dbuf ? 2 : 1;
+    p.acc_base = p.a_slots * kASlotCols;
     const SmemLayout lay = make_layout(false, n_pad, stages, stages_b);
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
@@ -938,6 +985,9 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.L = (int)db;
     p.stages = stages;
     p.stages_b = stages_b;
+    p.a_slots = 4;
+    p.acc_bufs = 1;
+    p.acc_base = 4 * kASlotCols;
     p.Z = Z;
     p.ldz = ldz;
     // One CTA = one feature group x one contiguous slice of rows; the TMEM accumulation chain is cut
