@@ -476,17 +476,30 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         // thin QR of Y (src/pca.rs:716), implicit: G = Y^T Y accumulated in f64 from the exact fp32 products,
         // P = R^-1 (Cholesky; Jacobi when rank deficient) so that Q = Y P is orthonormal to eps64 * cond(Y)^2.
         // B = Q^T Xc (src/pca.rs:681) = P^T (Y^T Xc): C' = Xc^T Y in one pass over X.
+        // After a power iteration Y = Xc Z with the replicated Z still in Zd, so G = Y^T Y = Z^T (Xc^T Y) = Z^T C':
+        // a small replicated product instead of another pass over Y (same ~eps32 relative accuracy as the
+        // fp32-accumulated pass over the panels it replaces; that pass remains for n_iter == 0).
+        bool gram_from_c = n_iter > 0;
+        if (const char* e = getenv("PETAL_GRAM_FROM_C")) gram_from_c = gram_from_c && atoi(e) != 0;
         if constexpr (sizeof(T) == 4) {
-            PETAL_CUDA(cudaMemsetAsync(G2, 0, (size_t)(l * l) * sizeof(double), ctx->stream));
-            DBuf<double> Gp(ctx, (size_t)(ly * ly));
-            Gp.zero();
-            launch_panel_gram(ctx, Y.p, n, (int)ly, Gp.p);
-            // compact ly x ly -> l x l
-            PETAL_CUDA(cudaMemcpy2DAsync(G2, (size_t)l * sizeof(double), Gp.p, (size_t)ly * sizeof(double),
-                                         (size_t)l * sizeof(double), (size_t)l, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (!gram_from_c) {
+                PETAL_CUDA(cudaMemsetAsync(G2, 0, (size_t)(l * l) * sizeof(double), ctx->stream));
+                DBuf<double> Gp(ctx, (size_t)(ly * ly));
+                Gp.zero();
+                launch_panel_gram(ctx, Y.p, n, (int)ly, Gp.p);
+                // compact ly x ly -> l x l
+                PETAL_CUDA(cudaMemcpy2DAsync(G2, (size_t)l * sizeof(double), Gp.p, (size_t)ly * sizeof(double),
+                                             (size_t)l * sizeof(double), (size_t)l, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
         }
         xty_pass(Cp);
-        allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
+        if (gram_from_c) {
+            allreduce_sum(ctx, Cp, (size_t)(d * l + 1));
+            gemm_atb<double>(ctx, Zd.p, l, l, nullptr, Cp, l, l, nullptr, d, G2);
+            launch_symmetrize(ctx, G2, l);
+        } else {
+            allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
+        }
         pc.mark("G = Y^T Y, C' = Xc^T Y");
         gram_to_orthonormalizer(ctx, G2, l, cutoff, kGramNoise, P.p);
     } else {
