@@ -45,6 +45,7 @@ struct petal_ctx {
     int64_t launches = 0;
     int f32_engine = 1;  // 0 = SIMT FFMA, 1 = tcgen05 3xTF32 where supported
     int f64_engine = 1;  // 0 = SIMT DFMA, 1 = DMMA (mma.sync f64) for Gram-shaped contractions
+    bool tc_precise = true;  // tcgen05 engine: cut the TMEM accumulation chains (fp32-accurate) unless a caller opts out
     std::string last_error;
     // optional per-kernel timing (CUDA events on the launch stream), see petal_ctx_profile_json
     bool profiling = false;

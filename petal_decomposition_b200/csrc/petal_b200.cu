@@ -438,25 +438,34 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     DBuf<T> Y1;
     PETAL_CUDA(cudaMemsetAsync(tvd, 0, sizeof(double), ctx->stream));
     if constexpr (sizeof(T) == 4) {
-        if (panel) tc::launch_tc_xb<float>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, Y.p, ly, tvd, true, Ylo.p);
+        // Only the passes that define the result (the last Y and C' = Xc^T Y) run with cut accumulation chains;
+        // the power iterations in between only have to keep the dominant subspace and use the faster long chains.
+        if (panel)
+            tc::launch_tc_xb<float>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, Y.p, ly, tvd, true, Ylo.p,
+                                    n_iter == 0 ? -1 : 0);
     }
     if (!panel) gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
 
     pc.mark("Y = Xc Omega");
     // power iterations (src/pca.rs:708-715): Z = Xc^T Y, re-orthonormalise, Y = Xc Z
     DBuf<double> Zd(ctx, (size_t)(d * l));
-    auto xty_pass = [&](double* out) {  // out[d x l] = Xc^T Y
+    auto xty_pass = [&](double* out, int precise) {  // out[d x l] = Xc^T Y
         if constexpr (sizeof(T) == 4) {
             if (panel) {
                 PETAL_CUDA(cudaMemsetAsync(out, 0, (size_t)(d * l) * sizeof(double), ctx->stream));
-                tc::launch_tc_atb(ctx, X.p, d, d, cm.mu, Y.p, ly, l, n, out, l, true, Ylo.p);
+                tc::launch_tc_atb(ctx, X.p, d, d, cm.mu, Y.p, ly, l, n, out, l, true, Ylo.p, nullptr, precise);
                 return;
             }
         }
         gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, ly, l, nullptr, n, out);
     };
+    // X^T Y: its truncation bias (unlike X Z's, which mostly rescales columns) tilts the subspace, and what the
+    // measured: even two long-chain passes at the start cost two digits on the trailing components, so all of them
+    // run with cut chains (PETAL_ATB_FAST_ITERS = number of leading iterations on the fast path, for experiments)
+    int64_t fast_atb_iters = 0;
+    if (const char* e = getenv("PETAL_ATB_FAST_ITERS")) fast_atb_iters = atoi(e);
     for (int64_t it = 0; it < n_iter; ++it) {
-        xty_pass(Zd.p);
+        xty_pass(Zd.p, it < fast_atb_iters ? 0 : -1);
         allreduce_sum(ctx, Zd.p, (size_t)(d * l));
         pc.mark("  Z = Xc^T Y");
         orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
@@ -464,7 +473,8 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         bool done = false;
         if constexpr (sizeof(T) == 4) {
             if (panel) {
-                tc::launch_tc_xb<double>(ctx, X.p, d, n, d, Zd.p, l, false, l, cm.mu, Y.p, ly, nullptr, true, Ylo.p);
+                tc::launch_tc_xb<double>(ctx, X.p, d, n, d, Zd.p, l, false, l, cm.mu, Y.p, ly, nullptr, true, Ylo.p,
+                                         it == n_iter - 1 ? -1 : 0);
                 done = true;
             }
         }
@@ -492,7 +502,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
                                              (size_t)l * sizeof(double), (size_t)l, cudaMemcpyDeviceToDevice, ctx->stream));
             }
         }
-        xty_pass(Cp);
+        xty_pass(Cp, -1);
         if (gram_from_c) {
             allreduce_sum(ctx, Cp, (size_t)(d * l + 1));
             gemm_atb<double>(ctx, Zd.p, l, l, nullptr, Cp, l, l, nullptr, d, G2);

@@ -189,9 +189,6 @@ struct TcParams {
     int L;                // valid output columns
     int stages;           // X ring depth (X tile + mu slice; released as soon as the transform has read it)
     int stages_b;         // B ring depth (B / Y tiles; released by the MMAs, or by the transform for row-major Y)
-    int a_slots;          // TMEM operand ring slots (3 or 4)
-    int acc_bufs;         // accumulator sets in TMEM (1 or 2)
-    int acc_base;         // first accumulator column (a_slots * 64)
     // tc_xb outputs
     float* Y;
     float* Ylo;           // tc_xb panel mode: second panel with y - tf32(y) (the B_lo operand of a later tc_atb)
@@ -258,8 +255,8 @@ __device__ __forceinline__ uint32_t bar_full_b(uint32_t base, int s) { return ba
 __device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (24 + (uint32_t)s); }
 __device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }  // 4 slots
 __device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (36 + (uint32_t)t); }
-__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, int b) { return base + 8u * (40 + 2 * (uint32_t)b); }   // 40, 42
-__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base, int b) { return base + 8u * (41 + 2 * (uint32_t)b); }  // 41, 43
+__device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, int b) { return base + 8u * (40 + (uint32_t)b); }   // 40 .. 42
+__device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base, int b) { return base + 8u * (47 + (uint32_t)b); }  // 47 .. 49
 __device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (44 + (uint32_t)t); }
 
 // ------------------------------------------------------------------------------------------
@@ -314,10 +311,28 @@ __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.syn
 template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// Kernel modes (template parameter MODE); everything derived from it is a compile-time constant - the transform and
+// MMA issue loops are instruction-bound enough that a runtime modulo in them costs 10-20 %.
+//   0  fast     : 4-slot operand ring, one accumulator set, one accumulation chain per group
+//   1  fast2    : tc_xb only, n_pad <= 80: 3-slot ring, two accumulator sets alternating per super-tile, the epilogue of
+//                 tile g drained inside the K loop of tile g+1
+//   2  precise  : accumulation chains cut (the tensor core adds into its accumulator with truncation):
+//                 tc_xb : 3-slot ring, two sets, chains of 4 K blocks
+//                 tc_atb: 4-slot ring, three one-M-tile buffers, chains of 4 K blocks staggered between the M tiles
+template <bool ATB, int MODE>
+struct ModeTraits {
+    static constexpr bool kCut = (MODE == 2);
+    static constexpr int kSlots = (!ATB && MODE != 0) ? 3 : 4;
+    static constexpr int kAccBase = kSlots * kASlotCols;
+    static constexpr int kAccBufs = ATB ? (MODE == 2 ? 3 : 1) : (MODE == 0 ? 1 : 2);
+    static constexpr bool kStagger = ATB && MODE == 2;
+    static constexpr int kChainKB = 4;  // tc_xb precise: K blocks per chain (48 accumulating MMAs)
+};
+
 // transform + epilogue role (warps 0 .. 15).  warp w: M tile (w >> 2) & 1, TMEM lane quarter w & 3,
 // K-block half w >> 3.  EPI: this warp also runs the epilogue (tc_xb: all; tc_atb: first half only -
 // they hold the register accumulators, hence the separate instantiation and register budget).
-template <bool ATB, int NP, bool PANEL>
+template <bool ATB, int NP, bool PANEL, int MODE>
 __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_ptr, const SmemLayout& L,
                                                uint32_t bars, uint32_t tmem_base, int warp, int lane, int n_pad,
                                                int S) {
@@ -334,7 +349,13 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
         double ss = 0.0;
         // tc_atb: the two warps of a lane-quarter pair split the accumulator columns in alternate 16-column chunks,
         // so each thread keeps at most ceil(NP/32) * 16 running sums in registers
-        constexpr int kAccChunks = ATB ? (NP / 16 + 1) / 2 : 1;
+        // tc_xb with chain cutting (n_pad <= 80): 3 chunks of 16 (panel) or 5 chunks of 8 (row-major) -> 48
+        using MT_ = ModeTraits<ATB, MODE>;
+        constexpr bool CUT = MT_::kCut;
+        constexpr int kSlots = MT_::kSlots;
+        constexpr int kAccBaseC = MT_::kAccBase;
+        constexpr int acc_bufs = MT_::kAccBufs;
+        constexpr int kAccChunks = ATB ? (NP / 16 + 1) / 2 : 3;  // tc_xb: only touched when CUT
         float racc[kAccChunks * 16];
 #pragma unroll
         for (int j = 0; j < kAccChunks * 16; ++j) racc[j] = 0.f;
@@ -354,17 +375,17 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 y_mu[u] = (p.mub_pad != nullptr && i < n_pad * 8) ? p.mub_pad[nn] : 0.f;
             }
         }
+        bool pend_on = false;
+        int64_t pend_row0 = 0;
+        // ======== fast mode (CUT == false): one chain per group ========
         // ---- tc_xb epilogue, drained one 16-column chunk at a time.  With two accumulator sets the drain of
         // super-tile g is deferred into the K loop of super-tile g+1 (one chunk after each of its first K blocks),
         // so the tensor pipe keeps running while Y is written.
-        const int acc_bufs = p.acc_bufs;
         const int xb_chunks = ATB ? 0 : (panel ? (n_pad - half * 16 + 31) / 32 : n_pad / 16);
-        bool pend_on = false;
-        int64_t pend_row0 = 0;
         uint32_t pend_gi = 0;
         int pend_next = 0;
         auto xb_drain_chunk = [&](int64_t row0, int buf, int j) {
-            const uint32_t acc_col = (uint32_t)(p.acc_base + buf * kMT * n_pad + mt * n_pad);
+            const uint32_t acc_col = (uint32_t)(kAccBaseC + buf * kMT * n_pad + mt * n_pad);
             if (panel) {
                 // panel-major Y [row block of 32][n_pad][32]: lane = row inside the block, so for each
                 // column the warp writes one full 128 B line.  The two warps of a lane-quarter pair
@@ -441,6 +462,152 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 pend_on = false;
             }
         };
+        // ======== precise mode (CUT == true) ========
+        // ---- accumulator hand-off.  The tensor core adds into its fp32 accumulator with truncation (bias ~ -2e-8
+        // per add), so accumulation chains are kept short: with two accumulator sets in TMEM (`cut`) a chain is
+        // p.chain_kb K blocks; each finished chain is added into fp32 registers (round to nearest) one K block
+        // later, while the MMAs already fill the other set.  tc_xb writes Y from the registers at the end of a
+        // super-tile, tc_atb sends the registers to global memory once per CTA.  With a single accumulator set
+        // (n_pad > 80) a chain is a whole group and tc_xb drains TMEM straight to global memory.
+        constexpr bool cut = true;
+        constexpr int chain_kb = MT_::kChainKB;
+        uint32_t chains = 0;  // chains handed to the MMA warps so far (both sides count alike)
+        bool pend_flush = false;
+        uint32_t pend_ch = 0;
+        // TMEM accumulator set -> += registers
+        auto drain_acc = [&](uint32_t acc_col) {
+            if constexpr (ATB) {
+#pragma unroll
+                for (int ch = 0; ch < kAccChunks; ++ch) {
+                    const int c0 = (2 * ch + half) * 16;
+                    if (c0 < NP) {
+                        uint32_t w[16];
+                        tmem_ld16(tmem_base + lane_field + acc_col + (uint32_t)c0, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) racc[ch * 16 + j] += __uint_as_float(w[j]);
+                    }
+                }
+            } else if (panel) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const int c0 = half * 16 + 32 * ch;
+                    if (c0 < n_pad) {
+                        uint32_t w[16];
+                        tmem_ld16(tmem_base + lane_field + acc_col + (uint32_t)c0, w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) racc[ch * 16 + j] += __uint_as_float(w[j]);
+                    }
+                }
+            } else {
+                const uint32_t acc16 = tmem_base + ((uint32_t)(q * 32 + half * 16) << 16) + acc_col;
+#pragma unroll
+                for (int ch = 0; ch < 5; ++ch) {
+                    if (16 * ch < n_pad) {
+                        uint32_t w[8];
+                        tmem_ld_16x256b_x2(acc16 + (uint32_t)(16 * ch), w);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) racc[ch * 8 + e] += __uint_as_float(w[e]);
+                    }
+                }
+            }
+        };
+        // one 16-column chunk of a tc_xb super-tile -> global memory; w = the chunk's values in this thread's layout
+        auto store_panel_chunk = [&](int64_t row0, int c0, const float* w) {
+            // panel-major Y [row block of 32][n_pad][32]: lane = row inside the block, so for each column the warp
+            // writes one full 128 B line.  Rows past n are written as zeros.
+            const int64_t r = row0 + mt * 128 + lrow;
+            const int64_t rblk = (row0 + mt * 128 + q * 32) >> 5;
+            if (rblk * 32 >= p.n) return;  // the panel buffer ends at the last partial row block
+            float* yb = p.Y + (rblk * n_pad) * 32 + lane;
+            float* yl = p.Ylo + (rblk * n_pad) * 32 + lane;
+            const bool valid = r < p.n;
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+                const float y = valid ? w[jj] : 0.f;
+                yb[(c0 + jj) * 32] = y;
+                yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
+            }
+        };
+        auto store_rowmajor_chunk = [&](int64_t row0, int c0, const float* w) {
+            // 16x256b pattern: four lanes hold 8 consecutive columns of one row, so every store instruction writes
+            // whole 32 B sectors (8 rows x 32 B).  This warp covers lanes 16*half .. 16*half+15 of its quarter.
+            const int t0 = lane & 3, t1 = lane >> 2;
+            const int64_t ra = row0 + mt * 128 + q * 32 + half * 16 + t1;
+            const int64_t rb = ra + 8;
+            const int ca = c0 + 2 * t0, cb = ca + 8;
+            if (p.y_vec) {
+                if (ra < p.n) {
+                    if (ca + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) = make_float2(w[0], w[1]);
+                    if (cb + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) = make_float2(w[4], w[5]);
+                }
+                if (rb < p.n) {
+                    if (ca + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) = make_float2(w[2], w[3]);
+                    if (cb + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) = make_float2(w[6], w[7]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int64_t r = (e & 2) ? rb : ra;
+                    const int c = ((e & 4) ? cb : ca) + (e & 1);
+                    if (r < p.n && c < p.ldy) p.Y[r * p.ldy + c] = w[e];
+                }
+            }
+        };
+        // tc_xb, registers -> Y for the super-tile starting at row0, registers cleared
+        auto flush_y = [&](int64_t row0) {
+            if (panel) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    if (half * 16 + 32 * ch < n_pad) store_panel_chunk(row0, half * 16 + 32 * ch, racc + ch * 16);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 5; ++ch)
+                    if (16 * ch < n_pad) store_rowmajor_chunk(row0, 16 * ch, racc + ch * 8);
+            }
+#pragma unroll
+            for (int j = 0; j < kAccChunks * 16; ++j) racc[j] = 0.f;
+        };
+        // tc_xb with a single accumulator set: TMEM -> global, chunk by chunk
+        auto xb_direct = [&](int64_t row0) {
+            const uint32_t acc_col = (uint32_t)(kAccBaseC + mt * n_pad);
+            if (panel) {
+                for (int c0 = half * 16; c0 < n_pad; c0 += 32) {
+                    uint32_t w[16];
+                    tmem_ld16(tmem_base + lane_field + acc_col + (uint32_t)c0, w);
+                    tmem_ld_wait();
+                    store_panel_chunk(row0, c0, reinterpret_cast<const float*>(w));
+                }
+            } else {
+                const uint32_t acc16 = tmem_base + ((uint32_t)(q * 32 + half * 16) << 16) + acc_col;
+                for (int c0 = 0; c0 < n_pad; c0 += 16) {
+                    uint32_t w[8];
+                    tmem_ld_16x256b_x2(acc16 + (uint32_t)c0, w);
+                    tmem_ld_wait();
+                    store_rowmajor_chunk(row0, c0, reinterpret_cast<const float*>(w));
+                }
+            }
+        };
+        constexpr bool stagger = MT_::kStagger;
+        int pend_kb = 0;
+        auto do_pending = [&]() {
+            // two full sets: chain c uses set c & 1.  staggered: chain j (of one M tile) uses buffer j % 3.
+            const int buf = stagger ? (int)(pend_ch % 3u) : (int)(pend_ch & 1u);
+            const uint32_t par = stagger ? ((pend_ch / 3u) & 1u) : ((pend_ch >> 1) & 1u);
+            const uint32_t acc_col = stagger ? (uint32_t)(kAccBaseC + buf * n_pad)
+                                             : (uint32_t)(kAccBaseC + buf * kMT * n_pad + mt * n_pad);
+            mbar_wait(bar_acc_full(bars, buf), par);
+            tc_fence_after();
+            if (ATB || cut) drain_acc(acc_col);
+            else xb_direct(pend_row0);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty(bars, buf));
+            if (!ATB && cut && pend_flush) flush_y(pend_row0);
+            pend_on = false;
+        };
         Group g;
         g.f0 = 0;
         for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
@@ -452,8 +619,8 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 const int s = (int)(it % (uint32_t)S);
                 const uint32_t ph = (it / (uint32_t)S) & 1u;
                 const uint32_t gran = 2u * it + (uint32_t)half;  // this warp's half K block
-                const int ta = (int)(gran % (uint32_t)p.a_slots);
-                const uint32_t pa = (gran / (uint32_t)p.a_slots) & 1u;
+                const int ta = (int)(gran % (uint32_t)kSlots);
+                const uint32_t pa = (gran / (uint32_t)kSlots) & 1u;
                 mbar_wait(bar_full(bars, s), ph);
                 if (warp == 0 && lane == 0) trace_ev(p, 3, it);
                 uint32_t v[16];
@@ -558,15 +725,44 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_a_ready(bars, ta));
                 if (warp == 0 && lane == 0) trace_ev(p, 6, it);
-                if (!ATB && pend_on && kb >= 1) xb_drain_step();  // previous super-tile, one chunk per K block
+                if constexpr (CUT) {
+                  if (stagger) {
+                    // tc_atb: chains of 4 K blocks per M tile, M tile 1 shifted by 2 K blocks, three accumulator buffers
+                    // rotating over the chains in start order (j = 2c + 1 for M tile 0, 2c for M tile 1).  A chain is
+                    // added into the registers two K blocks after it ended (its MMAs have completed by then), which
+                    // is before the buffer's next owner (chain j + 3) starts.  One group per CTA (host guarantees it).
+                    const int kbi = (int)kb;
+                    if (pend_on && kbi == pend_kb + 2) do_pending();
+                    const bool chain_end = (kb == g.kblocks - 1) || (((kbi + 2 * mt) & 3) == 3);
+                    if (chain_end) {
+                        if (pend_on) do_pending();
+                        pend_on = true;
+                        pend_ch = (mt == 0) ? (uint32_t)(2 * (kbi >> 2) + 1) : (uint32_t)(2 * ((kbi + 2) >> 2));
+                        pend_kb = kbi;
+                    }
+                  } else {
+                    const bool chain_end = (kb == g.kblocks - 1) || (((int)kb & (chain_kb - 1)) == chain_kb - 1);
+                    if (chain_end) {
+                        // the previous chain ended chain_kb K blocks ago: its MMAs have long completed, so this never
+                        // blocks, and the MMA warps need its accumulator set only for the chain after this one
+                        if (pend_on) do_pending();
+                        pend_on = true;
+                        pend_ch = chains++;
+                        pend_flush = (kb == g.kblocks - 1);
+                        pend_row0 = g.row0;
+                    }
+                  }
+                } else {
+                    if (!ATB && pend_on && kb >= 1) xb_drain_step();  // previous super-tile, one chunk per K block
+                }
             }
             if (!ATB && row_valid) ss += (double)((ss0 + ss1) + (ss2 + ss3));
 
-            // ---------------- epilogue for this group ----------------
+            if constexpr (!CUT) {
             if constexpr (ATB) {
                 mbar_wait(bar_acc_full(bars, 0), (uint32_t)gi & 1u);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + lane_field + (uint32_t)(p.acc_base + mt * n_pad);
+                const uint32_t acc = tmem_base + lane_field + (uint32_t)(kAccBaseC + mt * n_pad);
 #pragma unroll
                 for (int ch = 0; ch < kAccChunks; ++ch) {
                     const int c0 = (2 * ch + half) * 16;
@@ -590,9 +786,14 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 if (acc_bufs != 2)
                     while (pend_on) xb_drain_step();  // single accumulator set: drain now
             }
+            }
         }
-        if (!ATB)
-            while (pend_on) xb_drain_step();
+        if constexpr (CUT) {
+            if (pend_on) do_pending();
+        } else {
+            if (!ATB)
+                while (pend_on) xb_drain_step();
+        }
         if constexpr (ATB) {
             // the CTA's partial (256 features x L) -> global f64 accumulator
             const int64_t f = (int64_t)g.f0 + mt * 128 + lrow;
@@ -613,7 +814,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
     }
 }
 
-template <bool ATB, int NP, bool PANEL>
+template <bool ATB, int NP, bool PANEL, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -639,11 +840,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             mbar_init(bar_a_ready(bars, t), kTransformWarps / 2);  // the 8 warps that own this half of a K block
             mbar_init(bar_a_free(bars, t), kMT);
         }
-        mbar_init(bar_acc_full(bars, 0), kMT);
-        mbar_init(bar_acc_full(bars, 1), kMT);
+        // staggered tc_atb chains (acc_bufs == 3): a buffer belongs to one M tile at a time
+        for (int b = 0; b < 3; ++b) {
+            mbar_init(bar_acc_full(bars, b), ModeTraits<ATB, MODE>::kStagger ? 1 : kMT);
+            mbar_init(bar_acc_empty(bars, b), ModeTraits<ATB, MODE>::kStagger ? kTransformWarps / 2 : kTransformWarps);
+        }
         for (int t = 0; t < kYBufs; ++t) mbar_init(bar_y_free(bars, t), kMT);
-        mbar_init(bar_acc_empty(bars, 0), kTransformWarps);
-        mbar_init(bar_acc_empty(bars, 1), kTransformWarps);
         fence_barrier_init();
     }
     if (warp == kTransformWarps + 3) tmem_alloc(base + L.tmem_slot, kTmemCols);
@@ -719,15 +921,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             // every address / descriptor is warp-uniform; only the tcgen05 instructions are elected.
             const int mt = warp - (kTransformWarps + 1);
             const uint32_t idesc = make_idesc_tf32(n_pad, 0);
-            const uint32_t aslots = (uint32_t)p.a_slots;
+            using MT_ = ModeTraits<ATB, MODE>;
+            constexpr uint32_t aslots = (uint32_t)MT_::kSlots;
+            constexpr int kAccBaseC = MT_::kAccBase;
+            constexpr bool stagger = MT_::kStagger;
+            constexpr bool two_sets = (MT_::kAccBufs == 2);
+            constexpr bool cut2 = two_sets && MT_::kCut;  // tc_xb precise: chains of kChainKB K blocks
+            constexpr int chain_kb = MT_::kChainKB;
             uint32_t it = 0;
+            uint32_t chains = 0;   // accumulation chains started so far (same count as in the transform warps)
+            int abuf = 0;
+            uint32_t acc = 0;
             Group g;
             for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
-                const int abuf = (p.acc_bufs == 2) ? (int)(gi & 1) : 0;
-                const uint32_t acc = tmem_base + (uint32_t)(p.acc_base + abuf * kMT * n_pad + mt * n_pad);
-                mbar_wait(bar_acc_empty(bars, abuf), ((p.acc_bufs == 2) ? ((uint32_t)(gi >> 1) & 1u) : ((uint32_t)gi & 1u)) ^ 1u);
-                tc_fence_after();
-                for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
+                const int nkb = (int)g.kblocks;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    bool chain_start, chain_end;
+                    if constexpr (stagger) {
+                        // see transform_role: this M tile's chains, buffers rotate over the chains of both M tiles
+                        chain_start = (kb == 0) || (((kb + 2 * mt) & 3) == 0);
+                        chain_end = (kb == nkb - 1) || (((kb + 2 * mt) & 3) == 3);
+                        if (chain_start) {
+                            const uint32_t j = (mt == 0) ? (uint32_t)(2 * (kb >> 2) + 1) : (uint32_t)(2 * ((kb + 2) >> 2));
+                            abuf = (int)(j % 3u);
+                            acc = tmem_base + (uint32_t)(kAccBaseC + abuf * n_pad);
+                            mbar_wait(bar_acc_empty(bars, abuf), ((j / 3u) & 1u) ^ 1u);
+                            tc_fence_after();
+                        }
+                    } else {
+                        chain_start = (kb == 0) || (cut2 && (kb & (chain_kb - 1)) == 0);
+                        chain_end = (kb == nkb - 1) || (cut2 && (kb & (chain_kb - 1)) == chain_kb - 1);
+                        if (chain_start) {
+                            abuf = two_sets ? (int)(chains & 1u) : 0;
+                            acc = tmem_base + (uint32_t)(kAccBaseC + abuf * kMT * n_pad + mt * n_pad);
+                            mbar_wait(bar_acc_empty(bars, abuf), (two_sets ? ((chains >> 1) & 1u) : (chains & 1u)) ^ 1u);
+                            tc_fence_after();
+                            ++chains;
+                        }
+                    }
                     const int sb = (int)(it % (uint32_t)SB);
                     const uint32_t phb = (it / (uint32_t)SB) & 1u;
                     // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are TMA-loaded panels, or
@@ -764,7 +995,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                 const uint64_t dlo = dlo0 + (uint64_t)(ks * 2);
                                 const uint32_t a_hi = a_hi0 + (uint32_t)k2 * 8u;
                                 const uint32_t a_lo = a_hi + 16u;
-                                mma_tf32_ts(acc, a_lo, dhi, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                                mma_tf32_ts(acc, a_lo, dhi, idesc, (!chain_start || ks > 0) ? 1u : 0u);
                                 mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
                                 mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
                             }
@@ -778,14 +1009,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     }
                     __syncwarp();
                     if (mt == 0 && lane == 0) trace_ev(p, 2, it);
+                    if (chain_end) {
+                        if (elect_one()) tc_commit(bar_acc_full(bars, abuf));
+                        __syncwarp();
+                    }
                 }
-                if (elect_one()) tc_commit(bar_acc_full(bars, abuf));
-                __syncwarp();
             }
         }
     } else {
         // ================================ transform + epilogue ================================
-        transform_role<ATB, NP, PANEL>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
+        transform_role<ATB, NP, PANEL, MODE>(p, base_ptr, L, bars, tmem_base, warp, lane, n_pad, S);
     }
 
     tc_fence_before();
@@ -852,21 +1085,28 @@ inline CUtensorMap make_map_2d(const float* ptr, uint64_t inner, uint64_t outer,
 
 inline int round_up(int64_t v, int m) { return (int)(((v + m - 1) / m) * m); }
 
+// precise = -1: the context default (petal_ctx::tc_precise), PETAL_TC_PRECISE overrides everything (testing)
+inline bool want_precise(petal_ctx* ctx, int precise, const char* kind_env = nullptr) {
+    if (kind_env)
+        if (const char* e = getenv(kind_env)) return atoi(e) != 0;
+    if (const char* e = getenv("PETAL_TC_PRECISE")) return atoi(e) != 0;
+    return precise < 0 ? ctx->tc_precise : (precise != 0);
+}
 inline bool xb_supported(const void* A, int64_t lda, int64_t n, int64_t K, int64_t L) {
     return n >= 512 && K >= 32 && L >= 1 && L <= 128 && (lda % 4 == 0) && is_aligned16(A) && n < ((int64_t)1 << 31) &&
            K < ((int64_t)1 << 31);
 }
 
-template <bool ATB, int NP, bool PANEL>
+template <bool ATB, int NP, bool PANEL, int MODE>
 inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t smem) {
     static size_t cur = 0;
     if (smem > cur) {
-        PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP, PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP, PANEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = smem;
     }
     const char* trace_path = getenv("PETAL_TC_TRACE");
     if (trace_path == nullptr) {
-        tc_gemm_kernel<ATB, NP, PANEL><<<grid, kThreads, smem, ctx->stream>>>(p);
+        tc_gemm_kernel<ATB, NP, PANEL, MODE><<<grid, kThreads, smem, ctx->stream>>>(p);
         check_launch(ctx);
         return;
     }
@@ -876,7 +1116,7 @@ inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t sm
     DBuf<long long> tr(ctx, cnt);
     tr.zero();
     q.trace = tr.p;
-    tc_gemm_kernel<ATB, NP, PANEL><<<grid, kThreads, smem, ctx->stream>>>(q);
+    tc_gemm_kernel<ATB, NP, PANEL, MODE><<<grid, kThreads, smem, ctx->stream>>>(q);
     check_launch(ctx);
     std::vector<long long> h(cnt);
     PETAL_CUDA(cudaMemcpyAsync(h.data(), tr.p, cnt * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -898,7 +1138,7 @@ inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t sm
 template <typename TS>
 void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_t K, const TS* B, int64_t ldb,
                   bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq,
-                  bool y_panel = false, float* Y_lo_panel = nullptr) {
+                  bool y_panel = false, float* Y_lo_panel = nullptr, int precise = -1) {
     const int n_pad = round_up(L, 16);
     int stages = 0, stages_b = 0;
     if (!pick_stages(false, n_pad, false, stages, stages_b)) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
@@ -927,18 +1167,20 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     p.y_panel = y_panel ? 1 : 0;
     p.Ylo = Y_lo_panel;
     p.sumsq = sumsq;
-    // two accumulator sets (deferred epilogue) whenever they fit beside a 3-slot operand ring: 192 + 4 n_pad <= 512
-    const char* dbe = getenv("PETAL_XB_DBUF");
-    const bool dbuf = (n_pad <= 80) && !(dbe && dbe[0] == '0');
-    p.a_slots = dbuf ? 3 : 4;
-    p.acc_bufs = dbuf ? 2 : 1;
-    p.acc_base = p.a_slots * kASlotCols;
+    // mode (see ModeTraits): two accumulator sets need 192 + 4 n_pad <= 512
+    const bool two_sets_fit = (n_pad <= 80);
+    int mode = 0;
+    if (two_sets_fit && want_precise(ctx, precise, "PETAL_XB_PRECISE")) mode = 2;
     const SmemLayout lay = make_layout(false, n_pad, stages, stages_b);
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
     KTimer kt(ctx, K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny", (double)n * (K + L) * sizeof(float));
-    if (y_panel) launch_kernel<false, 0, true>(ctx, p, grid, lay.total);
-    else launch_kernel<false, 0, false>(ctx, p, grid, lay.total);
+    switch (mode * 2 + (y_panel ? 1 : 0)) {
+        case 0: launch_kernel<false, 0, false, 0>(ctx, p, grid, lay.total); break;
+        case 1: launch_kernel<false, 0, true, 0>(ctx, p, grid, lay.total); break;
+        case 4: launch_kernel<false, 0, false, 2>(ctx, p, grid, lay.total); break;
+        default: launch_kernel<false, 0, true, 2>(ctx, p, grid, lay.total); break;
+    }
 }
 
 inline bool atb_supported(const void* A, int64_t lda, int64_t da, const void* B, int64_t ldb, int64_t db, int64_t n) {
@@ -950,7 +1192,7 @@ inline bool atb_supported(const void* A, int64_t lda, int64_t da, const void* B,
 // b_panel: B is panel-major [ceil(n/32)][n_pad][32] (as written by launch_tc_xb with y_panel).
 inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t da, const float* mua, const float* B,
                           int64_t ldb, int64_t db, int64_t n, double* Z, int64_t ldz, bool b_panel = false,
-                          const float* B_lo_panel = nullptr, const float* mub = nullptr) {
+                          const float* B_lo_panel = nullptr, const float* mub = nullptr, int precise = -1) {
     const int n_pad = round_up(db, 16);
     int stages = 0, stages_b = 0;
     if (!pick_stages(true, n_pad, b_panel, stages, stages_b)) linalg_error("tc_atb: no pipeline configuration fits in shared memory");
@@ -985,32 +1227,47 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.L = (int)db;
     p.stages = stages;
     p.stages_b = stages_b;
-    p.a_slots = 4;
-    p.acc_bufs = 1;
-    p.acc_base = 4 * kASlotCols;
+    // fast: one accumulator set, chain = 1024 rows.  precise (n_pad <= 80): chains of 4 K blocks (48 accumulating MMAs),
+    // staggered between the two M tiles over three one-tile accumulator buffers, so the 4-slot operand ring stays
+    // (the truncating accumulation of the tensor core biases long chains, see transform_role)
+    const bool cut = (n_pad <= 80) && want_precise(ctx, precise, "PETAL_ATB_PRECISE");  // 256 + 3 n_pad <= 512
     p.Z = Z;
     p.ldz = ldz;
     // One CTA = one feature group x one contiguous slice of rows; the TMEM accumulation chain is cut
     // every 1024 rows (see the kernel comment).
     const int64_t max_slices = std::max<int64_t>(1, ctx->sm_count / fgroups);
     const int64_t slices = std::max<int64_t>(1, std::min<int64_t>(max_slices, ceil_div(n, 1024)));
-    p.chunk_rows = 1024;
     p.slice_rows = ceil_div(ceil_div(n, slices), 32) * 32;
+    p.chunk_rows = cut ? p.slice_rows : 1024;  // precise: chains are cut inside the kernel, one group per CTA
     p.fgroups = fgroups;
     p.dbg = getenv("PETAL_TC_DBG") ? atoi(getenv("PETAL_TC_DBG")) : 0;
     const SmemLayout lay = make_layout(true, n_pad, stages, stages_b, b_panel);
     const int grid = (int)(ceil_div(n, p.slice_rows) * fgroups);
     KTimer kt(ctx, da >= 256 ? "tc_atb_f32" : "tc_atb_f32_skinny", (double)n * (da + db) * sizeof(float));
+#define PETAL_ATB_CASE(NPV)                                                                  \
+    case NPV:                                                                                \
+        if (cut) {                                                                           \
+            if (b_panel) launch_kernel<true, (NPV <= 80 ? NPV : 80), true, 2>(ctx, p, grid, lay.total);   \
+            else launch_kernel<true, (NPV <= 80 ? NPV : 80), false, 2>(ctx, p, grid, lay.total);          \
+        } else {                                                                             \
+            if (b_panel) launch_kernel<true, NPV, true, 0>(ctx, p, grid, lay.total);     \
+            else launch_kernel<true, NPV, false, 0>(ctx, p, grid, lay.total);            \
+        }                                                                                    \
+        break;
     switch (n_pad) {
-        case 16: if (b_panel) launch_kernel<true, 16, true>(ctx, p, grid, lay.total); else launch_kernel<true, 16, false>(ctx, p, grid, lay.total); break;
-        case 32: if (b_panel) launch_kernel<true, 32, true>(ctx, p, grid, lay.total); else launch_kernel<true, 32, false>(ctx, p, grid, lay.total); break;
-        case 48: if (b_panel) launch_kernel<true, 48, true>(ctx, p, grid, lay.total); else launch_kernel<true, 48, false>(ctx, p, grid, lay.total); break;
-        case 64: if (b_panel) launch_kernel<true, 64, true>(ctx, p, grid, lay.total); else launch_kernel<true, 64, false>(ctx, p, grid, lay.total); break;
-        case 80: if (b_panel) launch_kernel<true, 80, true>(ctx, p, grid, lay.total); else launch_kernel<true, 80, false>(ctx, p, grid, lay.total); break;
-        case 96: if (b_panel) launch_kernel<true, 96, true>(ctx, p, grid, lay.total); else launch_kernel<true, 96, false>(ctx, p, grid, lay.total); break;
-        case 112: if (b_panel) launch_kernel<true, 112, true>(ctx, p, grid, lay.total); else launch_kernel<true, 112, false>(ctx, p, grid, lay.total); break;
-        default: if (b_panel) launch_kernel<true, 128, true>(ctx, p, grid, lay.total); else launch_kernel<true, 128, false>(ctx, p, grid, lay.total); break;
+        PETAL_ATB_CASE(16)
+        PETAL_ATB_CASE(32)
+        PETAL_ATB_CASE(48)
+        PETAL_ATB_CASE(64)
+        PETAL_ATB_CASE(80)
+        PETAL_ATB_CASE(96)
+        PETAL_ATB_CASE(112)
+        default:
+            if (b_panel) launch_kernel<true, 128, true, 0>(ctx, p, grid, lay.total);
+            else launch_kernel<true, 128, false, 0>(ctx, p, grid, lay.total);
+            break;
     }
+#undef PETAL_ATB_CASE
 }
 
 }  // namespace tc
