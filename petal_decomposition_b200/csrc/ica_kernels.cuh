@@ -8,7 +8,7 @@
 // (lanes = rows) and, transposed through the transform warps, as the A operand of the second MMA
 // (lanes = features); G never leaves the SM (TMEM -> registers -> shared-memory operand tiles).
 // Both contractions are 3xTF32 (hi/lo split, fp32 accumulate in TMEM); the H accumulator chain is cut
-// every 8 tiles (1024 rows) into fp32 registers, and only the CTA's totals go to global memory (f64 atomics).
+// every tile (128 rows) into fp32 registers, and only the CTA's totals go to global memory (f64 atomics).
 //
 // Warp roles (32 warps):
 //   0-15  row warps     : lane quarter q = w & 3, 16-column group cq = w >> 2
@@ -37,7 +37,7 @@ constexpr int kXStage = kRows * kD * 4;    // 32 KB: two [128 rows][32 floats] S
 constexpr int kXStages = 3;
 constexpr int kWTile = kNC * 128;          // 8 KB: [64 comps][32 k] K-major SWIZZLE_128B
 constexpr int kGTile = kNC * 128;          // 8 KB: [64 comps][32 rows]
-constexpr int kFlushTiles = 8;
+constexpr int kFlushTiles = 1;   // H chain = one tile (48 accumulating MMAs): the tensor core truncates on accumulate; the drain is off the critical path
 // TMEM columns
 constexpr int kA1 = 0;                     // [hi 64 | lo 64]        lanes = rows
 constexpr int kA2 = 128;                   // [hi 128 | lo 128]      lanes = features

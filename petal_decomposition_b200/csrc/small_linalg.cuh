@@ -48,13 +48,14 @@ __device__ __forceinline__ void rr_pair(int me, int s, int i, int& p, int& q) {
 // absolute noise eps * lambda_max from the start, so two small rows cannot be made orthogonal
 // beyond that floor - without the floor the sweep loop never reports convergence.
 __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, double gamma, double tol, double noise,
-                                                double& c, double& s) {
+                                                double& c, double& s, double* t_out = nullptr) {
     const double na = sqrt(alpha), nb = sqrt(beta);
     if (!(fabs(gamma) > tol * na * nb + noise * (na + nb))) return false;  // also false for NaN/zero rows
     double zeta = (beta - alpha) / (2.0 * gamma);
     double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     c = rsqrt(1.0 + t * t);
     s = c * t;
+    if (t_out) *t_out = t;
     return true;
 }
 
@@ -105,6 +106,15 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
     const int gid = tid >> 4, gl = tid & 15, ngroups = kJacobiSmemThreads / 16;
     const unsigned gmask = 0xFFFFu << (lane & 16);
     for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
+        // squared row norms: recomputed exactly once per sweep, then carried through the rotations
+        // (|a'|^2 = |a|^2 - t g, |b'|^2 = |b|^2 + t g), so a step needs one inner product instead of three
+        for (int j = warp; j < m; j += nwarps) {
+            double a = 0.0;
+            for (int e = lane; e < len; e += 32) a += M[(size_t)j * len + e] * M[(size_t)j * len + e];
+            a = warp_sum(a);
+            if (lane == 0) nrm[j] = a;
+        }
+        __syncthreads();
         for (int step = 0; step < me - 1; ++step) {
             for (int pi = gid; pi < me / 2; pi += ngroups) {
                 int p, q;
@@ -112,18 +122,17 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
                 if (q >= m) continue;
                 double* mp = M + (size_t)p * len;
                 double* mq = M + (size_t)q * len;
-                double al = 0.0, be = 0.0, ga = 0.0;
-                for (int e = gl; e < len; e += 16) {
-                    double x = mp[e], y = mq[e];
-                    al += x * x;
-                    be += y * y;
-                    ga += x * y;
-                }
-                al = group16_sum(al, gmask);
-                be = group16_sum(be, gmask);
+                double ga = 0.0;
+                for (int e = gl; e < len; e += 16) ga += mp[e] * mq[e];
                 ga = group16_sum(ga, gmask);
-                double c, s;
-                if (!jacobi_rotation(al, be, ga, tol, noise, c, s)) continue;
+                const double al = nrm[p], be = nrm[q];
+                double c, s, t;
+                if (!jacobi_rotation(al, be, ga, tol, noise, c, s, &t)) continue;
+                __syncwarp(gmask);  // every lane of the group has read nrm[p], nrm[q]
+                if (gl == 0) {
+                    nrm[p] = fmax(al - t * ga, 0.0);
+                    nrm[q] = be + t * ga;
+                }
                 for (int e = gl; e < len; e += 16) {
                     double x = mp[e], y = mq[e];
                     mp[e] = c * x - s * y;
@@ -233,6 +242,117 @@ jacobi_step_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
     if (tid == 0) *rotated = 1;
 }
 
+// Persistent multi-CTA engine: all sweeps in one cooperative launch.  Every CTA takes the pairs blockIdx.x,
+// blockIdx.x + gridDim.x, ... of a round-robin step; steps are separated by a grid-wide barrier (one atomic
+// counter; cooperative launch guarantees co-residency).  Squared row norms are recomputed once per sweep and
+// carried through the rotations, so a step costs one inner product per pair.  rot[sweep] is raised by any
+// rotation; a sweep without rotations ends the factorization.  info[0] = sweeps used.
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int)(v - target) < 0);
+        __threadfence();  // acquire side: later loads of this CTA (ordered behind the barrier below) see the other CTAs' rows
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ J, double* __restrict__ nrm2, int me,
+                   int max_sweeps, double tol, double noise_rel, unsigned* __restrict__ bar, int* __restrict__ rot,
+                   int* __restrict__ info) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double red[8];
+    __shared__ double bc[3];
+    unsigned target = 0;
+    auto row_norm2 = [&](int j) {  // block-wide, result in bc[0] for every thread after the sync
+        double a = 0.0;
+        for (int e = tid; e < len; e += 256) {
+            const double x = M[(size_t)j * len + e];
+            a += x * x;
+        }
+        a = warp_sum(a);
+        __syncthreads();
+        if (lane == 0) red[warp] = a;
+        __syncthreads();
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sacc += red[w];
+        return sacc;
+    };
+    double noise = 0.0;
+    int sweeps = 0;
+    for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
+        for (int j = blockIdx.x; j < m; j += gridDim.x) {
+            const double a = row_norm2(j);
+            if (tid == 0) nrm2[j] = a;
+        }
+        grid_barrier(bar, target);
+        if (sweep == 0) {  // input-noise floor from the largest row norm
+            double amax = 0.0;
+            for (int j = tid; j < m; j += 256) amax = fmax(amax, nrm2[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            __syncthreads();
+            if (lane == 0) red[warp] = amax;
+            __syncthreads();
+            amax = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) amax = fmax(amax, red[w]);
+            noise = noise_rel * sqrt(amax);
+        }
+        for (int step = 0; step < me - 1; ++step) {
+            for (int pi = blockIdx.x; pi < me / 2; pi += gridDim.x) {
+                int p, q;
+                rr_pair(me, step, pi, p, q);
+                if (q >= m) continue;
+                double* mp = M + (size_t)p * len;
+                double* mq = M + (size_t)q * len;
+                double ga = 0.0;
+                for (int e = tid; e < len; e += 256) ga += mp[e] * mq[e];
+                ga = warp_sum(ga);
+                __syncthreads();
+                if (lane == 0) red[warp] = ga;
+                __syncthreads();
+                ga = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) ga += red[w];
+                const double al = nrm2[p], be = nrm2[q];
+                double c, s, t;
+                if (!jacobi_rotation(al, be, ga, tol, noise, c, s, &t)) continue;  // block-uniform
+                __syncthreads();
+                if (tid == 0) {
+                    nrm2[p] = fmax(al - t * ga, 0.0);
+                    nrm2[q] = be + t * ga;
+                    rot[sweep] = 1;
+                }
+                for (int e = tid; e < len; e += 256) {
+                    const double x = mp[e], y = mq[e];
+                    mp[e] = c * x - s * y;
+                    mq[e] = s * x + c * y;
+                }
+                double* jp = J + (size_t)p * m;
+                double* jq = J + (size_t)q * m;
+                for (int e = tid; e < m; e += 256) {
+                    const double x = jp[e], y = jq[e];
+                    jp[e] = c * x - s * y;
+                    jq[e] = s * x + c * y;
+                }
+            }
+            grid_barrier(bar, target);
+        }
+        sweeps = sweep + 1;
+        if (reinterpret_cast<volatile int*>(rot)[sweep] == 0) break;  // written before the last barrier of the sweep: same value in every CTA
+    }
+    if (blockIdx.x == 0 && tid == 0 && info) info[0] = sweeps;
+    (void)bc;
+}
+
 __global__ void __launch_bounds__(256)
 row_norm_kernel(const double* __restrict__ M, int m, int len, double* __restrict__ nrm) {
     const int j = blockIdx.x;
@@ -334,6 +454,42 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     check_launch(ctx);
     const int me = (int)((m + 1) & ~(int64_t)1);
     int sweeps = 0;
+    // persistent cooperative kernel (one launch for all sweeps) when the device supports it
+    static int coop_ok = -1;
+    static int coop_max_ctas = 0;
+    if (coop_ok < 0) {
+        int dev = 0, attr = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_coop_kernel, 256, 0);
+        coop_max_ctas = per_sm * ctx->sm_count;
+        coop_ok = (attr != 0 && coop_max_ctas > 0 && getenv("PETAL_JACOBI_COOP_OFF") == nullptr) ? 1 : 0;
+    }
+    if (coop_ok == 1 && m > 1) {
+        DBuf<unsigned> bar(ctx, 1);
+        DBuf<int> rot(ctx, (size_t)max_sweeps + 1);
+        bar.zero();
+        rot.zero();
+        int grid = std::min<int>(me / 2, coop_max_ctas);
+        grid = std::max(grid, 1);
+        double* Mp = M.p;
+        double* Jp = J.p;
+        double* np = nrm.p;
+        int mi = (int)m, li = (int)len, ms = max_sweeps;
+        double tl = tol, nr = input_noise_rel;
+        unsigned* bp = bar.p;
+        int* rp = rot.p;
+        int* ip = rot.p + max_sweeps;
+        int mee = me;
+        void* args[] = {&Mp, &mi, &li, &Jp, &np, &mee, &ms, &tl, &nr, &bp, &rp, &ip};
+        PETAL_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_coop_kernel, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
+        check_launch(ctx);
+        row_norm_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, nrm.p);
+        check_launch(ctx);
+        sort_scatter_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, J.p, nrm.p, (int)m, (int)len, Aout, Jt, sig);
+        check_launch(ctx);
+        return -1;
+    }
     for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
         rotated.zero();
         for (int step = 0; step < me - 1; ++step) {
