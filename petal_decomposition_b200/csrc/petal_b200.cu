@@ -284,16 +284,21 @@ void orthonormalize_columns(petal_ctx* ctx, double* Z, int64_t rows, int64_t l, 
 // max-|.| entry of the score column (same sign as the U column since sigma >= 0), first row
 // wins, across all ranks; flips score columns and component rows.
 template <typename T>
-void flip_signs(petal_ctx* ctx, T* scores, int64_t n, int64_t k, T* comps, int64_t d, bool scores_wanted = true) {
+void flip_signs(petal_ctx* ctx, T* scores, int64_t n, int64_t k, T* comps, int64_t d, bool scores_wanted = true,
+                double* have_local3 = nullptr) {
     if (k == 0) return;
-    DBuf<double> local3(ctx, (size_t)(k * 3));
-    launch_colabsmax<T>(ctx, scores, n, k, k, local3.p);
-    double* flip3 = local3.p;
+    DBuf<double> local3;
+    if (have_local3 == nullptr) {
+        local3.alloc(ctx, (size_t)(k * 3));
+        launch_colabsmax<T>(ctx, scores, n, k, k, local3.p);
+        have_local3 = local3.p;
+    }
+    double* flip3 = have_local3;
     DBuf<double> gathered, out3;
     if (ctx->world > 1) {
         gathered.alloc(ctx, (size_t)(ctx->world * k * 3));
         out3.alloc(ctx, (size_t)(k * 3));
-        allgather(ctx, local3.p, gathered.p, (size_t)(k * 3));
+        allgather(ctx, have_local3, gathered.p, (size_t)(k * 3));
         combine_absmax_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(gathered.p, ctx->world, k, out3.p);
         launch1(ctx);
         flip3 = out3.p;
@@ -576,22 +581,28 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         launch1(ctx);
         DBuf<T> scores_tmp;
         T* scores_dev = scores.p;
-        if (!scores_dev) {
-            scores_tmp.alloc(ctx, (size_t)(n * k));
-            scores_dev = scores_tmp.p;
-        }
+        DBuf<double> absmax3;
         bool done = false;
         if constexpr (sizeof(T) == 4) {
             if (panel) {
+                // scores from the panels; the column |max| / row / sign triples of svd_flip come out of the same
+                // kernel, and when the caller did not ask for the scores they are never written
                 DBuf<float> Sf(ctx, (size_t)(l * k));
                 launch_cast<double, float>(ctx, S.p, Sf.p, l * k);
-                launch_panel_xb(ctx, Y.p, n, (int)ly, (int)l, Sf.p, (int)k, scores_dev, k);
+                absmax3.alloc(ctx, (size_t)(k * 3));
+                launch_panel_xb(ctx, Y.p, n, (int)ly, (int)l, Sf.p, (int)k, scores_dev, k, absmax3.p);
                 done = true;
             }
         }
-        if (!done) gemm_xb_b64<T>(ctx, Y1.p, ly, n, l, S.p, k, k, nullptr, scores_dev, k);
+        if (!done) {
+            if (!scores_dev) {
+                scores_tmp.alloc(ctx, (size_t)(n * k));
+                scores_dev = scores_tmp.p;
+            }
+            gemm_xb_b64<T>(ctx, Y1.p, ly, n, l, S.p, k, k, nullptr, scores_dev, k);
+        }
         pc.mark("scores = Y1 S");
-        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores);  // svd_flip, src/pca.rs:684
+        flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores, absmax3.p);  // svd_flip, src/pca.rs:684
         pc.mark("svd_flip");
         if (sing) launch_cast<double, T>(ctx, sigB.p, sing.p, k);
     }

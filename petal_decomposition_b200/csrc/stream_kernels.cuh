@@ -658,6 +658,20 @@ void launch_atb(petal_ctx* ctx, AtbParams<T> p) {
 //   panel_xb   : out[n x k] (row-major) = Y * S,  S[l x k] row-major
 // Skinny, Y-sized passes of the randomized-PCA epilogue (G1 = Y^T Y, scores = Q U_B Sigma).
 // ------------------------------------------------------------------------------------------
+struct AbsMax {
+    double a;     // |value|
+    double sgn;   // +1 / -1 (f64::signum semantics: -0.0 -> -1)
+    int64_t idx;  // row index (local)
+};
+
+__device__ __forceinline__ bool absmax_better(const AbsMax& x, const AbsMax& y) {
+    // first maximum wins (reference src/pca.rs:830 `abs <= absmax -> continue`)
+    return x.a > y.a || (x.a == y.a && x.idx < y.idx);
+}
+
+__global__ void colabsmax_final_kernel(const AbsMax* __restrict__ partial, int64_t chunks, int64_t k,
+                                       double* __restrict__ out3);
+
 template <int NP>
 __global__ void __launch_bounds__(256)
 panel_gram_kernel(const float* __restrict__ Yp, int64_t nblocks, int64_t blocks_per_cta, double* __restrict__ G) {
@@ -741,7 +755,7 @@ inline void launch_panel_gram(petal_ctx* ctx, const float* Yp, int64_t n, int np
 template <int KV>
 __global__ void __launch_bounds__(256)
 panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const float* __restrict__ S, int k,
-                float* __restrict__ out, int64_t ldo) {
+                float* __restrict__ out /* nullable */, int64_t ldo, AbsMax* __restrict__ partial /* nullable */) {
     extern __shared__ float psm[];
     constexpr int KP = 32 * KV;
     float* Ss = psm;                   // [l][KP]
@@ -754,6 +768,15 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
     const int64_t nblocks = (n + 31) / 32;
     const int64_t npairs = (nblocks + 1) / 2;
     const int i0 = tid >> 5, j0 = tid & 31;
+    // per column (max |score|, first row, sign) over the rows this thread produces: the u-based sign flip
+    // (reference src/pca.rs:815-850) needs it, and taking it here saves re-reading the scores
+    AbsMax best[KV];
+#pragma unroll
+    for (int v = 0; v < KV; ++v) {
+        best[v].a = -1.0;
+        best[v].sgn = 1.0;
+        best[v].idx = INT64_MAX;
+    }
     for (int64_t pb = blockIdx.x; pb < npairs; pb += gridDim.x) {
         __syncthreads();
         for (int h = 0; h < 2; ++h) {
@@ -786,14 +809,47 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
             if (r < n) {
 #pragma unroll
                 for (int v = 0; v < KV; ++v)
-                    if (KV * j0 + v < k) out[r * ldo + KV * j0 + v] = acc[u][v];
+                    if (KV * j0 + v < k) {
+                        if (out != nullptr) out[r * ldo + KV * j0 + v] = acc[u][v];
+                        if (partial != nullptr) {
+                            const double a = fabs((double)acc[u][v]);
+                            if (a > best[v].a || (a == best[v].a && r < best[v].idx)) {
+                                best[v].a = a;
+                                best[v].sgn = signbit(acc[u][v]) ? -1.0 : 1.0;
+                                best[v].idx = r;
+                            }
+                        }
+                    }
+            }
+        }
+    }
+    if (partial != nullptr) {
+        // combine the 8 row groups of the CTA (the operand staging area is free now)
+        __syncthreads();
+        AbsMax* red = reinterpret_cast<AbsMax*>(psm);  // [8][32 * KV]
+#pragma unroll
+        for (int v = 0; v < KV; ++v) red[i0 * (32 * KV) + KV * j0 + v] = best[v];
+        __syncthreads();
+        if (i0 == 0) {
+#pragma unroll
+            for (int v = 0; v < KV; ++v) {
+                const int col = KV * j0 + v;
+                if (col < k) {
+                    AbsMax b = red[col];
+                    for (int y = 1; y < 8; ++y) {
+                        const AbsMax c = red[y * (32 * KV) + col];
+                        if (absmax_better(c, b)) b = c;
+                    }
+                    partial[(int64_t)blockIdx.x * k + col] = b;
+                }
             }
         }
     }
 }
 
+// out (n x k, row-major) may be null when only absmax3 (k x 3: |max|, first local row, sign) is wanted
 inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, int l, const float* S, int k,
-                            float* out, int64_t ldo) {
+                            float* out, int64_t ldo, double* absmax3 = nullptr) {
     if (n == 0 || k == 0) return;
     const int kv = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
     size_t smem = ((size_t)l * 32 * kv + 65 * (size_t)np) * sizeof(float);
@@ -806,11 +862,20 @@ inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, 
     }
     const int64_t nblocks = ceil_div(n, 32);
     const int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->sm_count * 4);
-    KTimer kt(ctx, "panel_xb_f32", (double)n * (np + k) * sizeof(float));
-    if (k <= 32) panel_xb_kernel<1><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo);
-    else if (k <= 64) panel_xb_kernel<2><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo);
-    else panel_xb_kernel<4><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo);
-    check_launch(ctx);
+    smem = std::max(smem, (size_t)8 * 32 * kv * sizeof(AbsMax));
+    DBuf<AbsMax> partial;
+    if (absmax3 != nullptr) partial.alloc(ctx, (size_t)grid * k);
+    {
+        KTimer kt(ctx, "panel_xb_f32", (double)n * (np + (out ? k : 0)) * sizeof(float));
+        if (k <= 32) panel_xb_kernel<1><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
+        else if (k <= 64) panel_xb_kernel<2><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
+        else panel_xb_kernel<4><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
+        check_launch(ctx);
+    }
+    if (absmax3 != nullptr) {
+        colabsmax_final_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(partial.p, grid, k, absmax3);
+        check_launch(ctx);
+    }
 }
 
 __global__ void symmetrize_kernel(double* C, int64_t d, int64_t ldc) {
@@ -890,17 +955,6 @@ void launch_nonlin(petal_ctx* ctx, T* U, int64_t n, int64_t nc, int64_t ld, int 
 // ------------------------------------------------------------------------------------------
 // colabsmax : per column of S[n x k]: (max |s|, first row attaining it, sign of that entry)
 // ------------------------------------------------------------------------------------------
-struct AbsMax {
-    double a;     // |value|
-    double sgn;   // +1 / -1 (f64::signum semantics: -0.0 -> -1)
-    int64_t idx;  // row index (local)
-};
-
-__device__ __forceinline__ bool absmax_better(const AbsMax& x, const AbsMax& y) {
-    // first maximum wins (reference src/pca.rs:830 `abs <= absmax -> continue`)
-    return x.a > y.a || (x.a == y.a && x.idx < y.idx);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 colabsmax_kernel(const T* __restrict__ S, int64_t n, int64_t k, int64_t ld, AbsMax* __restrict__ partial,
