@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpetal_b200.so")
 SOURCES = ["petal_b200.cu", "rng.cpp"]
-HEADERS = ["common.cuh", "stream_kernels.cuh", "small_linalg.cuh", "comm.cuh", "tc_kernels.cuh",
-           os.path.join("..", "..", "include", "petal_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + [
+    os.path.join("..", "..", "include", "petal_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -10,14 +10,14 @@
 // Both contractions are 3xTF32 (hi/lo split, fp32 accumulate in TMEM); the H accumulator chain is cut
 // every tile (128 rows) into fp32 registers, and only the CTA's totals go to global memory (f64 atomics).
 //
-// Warp roles (32 warps):
+// Warp roles (22 warps):
 //   0-15  row warps     : lane quarter q = w & 3, 16-column group cq = w >> 2
-//                         transform-A (x - mu, hi/lo -> TMEM A1), epilogue-1 (U -> g -> smem G tiles, g' sums)
-//   16-31 with (w & 3) < 2: feature warps, q = w & 3 (features 0-63), row quarter rq = (w - 16) >> 2
-//                         transform-B (transposed x - mu, hi/lo -> TMEM A2), H flush into registers, final atomics
+//                         transform-A (x - mu, hi/lo -> TMEM A1), epilogue-1 (U -> g -> smem G tiles, g' sums);
+//                         the warps of lane quarters 0, 1 also drain the H accumulator (lanes = features)
+//   16,17,20,21 feature warps: q = w & 3 (features 0-63), quarter tiles (w - 16) >> 2 and + 2
+//                         transform-B (transposed x - mu, hi/lo -> the TMEM A2 ring)
 //   18    TMA producer  (X tile ring; W~ operand tiles once)
 //   19    MMA issuer + TMEM allocation
-//   others idle
 #pragma once
 #include "tc_kernels.cuh"
 
@@ -29,19 +29,20 @@ using namespace tc;
 constexpr int kRows = 128;                 // rows per tile
 constexpr int kD = 64;                     // padded features
 constexpr int kNC = 64;                    // padded components
-constexpr int kThreadsIca = 1024;
-constexpr int kRowWarps = 16;                // warps 0-15
-constexpr int kFeatWarps = 8;                // warps 16-31 with (w & 3) < 2
+constexpr int kThreadsIca = 704;           // 22 warps: 88 registers per thread
+constexpr int kRowWarps = 16;              // warps 0-15
+constexpr int kFeatWarps = 4;              // warps 16, 17, 20, 21 (TMEM lane quarters 0, 1 = features 0-63)
 constexpr int kTmaWarp = 18, kMmaWarp = 19;
 constexpr int kXStage = kRows * kD * 4;    // 32 KB: two [128 rows][32 floats] SWIZZLE_128B sub-tiles
-constexpr int kXStages = 3;
+constexpr int kXStages = 2;
 constexpr int kWTile = kNC * 128;          // 8 KB: [64 comps][32 k] K-major SWIZZLE_128B
 constexpr int kGTile = kNC * 128;          // 8 KB: [64 comps][32 rows]
-constexpr int kFlushTiles = 1;   // H chain = one tile (48 accumulating MMAs): the tensor core truncates on accumulate; the drain is off the critical path
-// TMEM columns
-constexpr int kA1 = 0;                     // [hi 64 | lo 64]        lanes = rows
-constexpr int kA2 = 128;                   // [hi 128 | lo 128]      lanes = features
-constexpr int kAccU = 384;                 // 64 columns
+constexpr int kGBuf = 8 * kGTile;          // one G buffer: hi tiles 0-3, lo tiles 4-7 (64 KB); two buffers
+// TMEM columns (all 512)
+constexpr int kA1 = 0;                     // [hi 64 | lo 64]                          lanes = rows
+constexpr int kA2 = 128;                   // ring of 3 quarter-tile slots [hi 32 | lo 32]  lanes = features
+constexpr int kA2Slots = 3;
+constexpr int kAccU = 320;                 // two U accumulators of 64 columns
 constexpr int kAccH = 448;                 // 64 columns
 
 struct IcaParams {
@@ -57,19 +58,19 @@ struct IcaParams {
     long long* trace;     // optional clock64 timeline of CTA 0 (PETAL_ICA_TRACE)
 };
 
-// smem carve-up (offsets from a 1024 B aligned base)
+// smem carve-up (offsets from a 1024 B aligned base): 64 + 32 + 128 KB
 constexpr uint32_t kOffX = 0;
 constexpr uint32_t kOffW = kOffX + kXStages * kXStage;       // W hi: 2 tiles, W lo: 2 tiles
-constexpr uint32_t kOffG = kOffW + 4 * kWTile;               // G hi: 4 tiles, G lo: 4 tiles
-constexpr uint32_t kOffMu = kOffG + 8 * kGTile;
+constexpr uint32_t kOffG = kOffW + 4 * kWTile;               // two G buffers
+constexpr uint32_t kOffMu = kOffG + 2 * kGBuf;
 constexpr uint32_t kOffBars = kOffMu + 256;
 constexpr uint32_t kOffSlot = kOffBars + 32 * 8;
 constexpr uint32_t kSmemIca = kOffSlot + 16 + 1024;
 
 __device__ __forceinline__ uint32_t ib(uint32_t bars, int i) { return bars + 8u * (uint32_t)i; }
 // barrier ids
-constexpr int B_XFULL = 0, B_XEMPTY = 3, B_WFULL = 6, B_A1 = 7, B_A2 = 8, B_UFULL = 9, B_UEMPTY = 10, B_GREADY = 11,
-              B_TILEFREE = 12, B_HFULL = 13, B_HEMPTY = 14;
+constexpr int B_XFULL = 0, B_XEMPTY = 2, B_WFULL = 4, B_A1 = 5, B_UFULL = 6, B_UEMPTY = 8, B_GREADY = 10, B_GFREE = 12,
+              B_A2READY = 14, B_A2FREE = 17, B_HFULL = 20, B_HEMPTY = 21;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -111,6 +112,11 @@ __device__ __forceinline__ void ica_trace(const IcaParams& p, int ev, uint32_t i
     if (p.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceTiles) p.trace[ev * kTraceTiles + it] = clock64();
 }
 
+// Software pipeline (tile index t per CTA; tensor pipe order M1(0), M1(1), M2(0), M1(2), M2(1), ...):
+//   M1(t): U[t & 1] = A1 * W~^T                    A1 (TMEM) written by the row warps from X(t)
+//   epi(t): U -> g -> G[t & 1] (smem operand tiles)  row warps, while M2(t-1) runs
+//   M2(t): H^T = A2 * G[t & 1], four quarter tiles   A2 ring slots written by the feature warps from X(t)
+//   H is drained into registers every tile (row warps of lane quarters 0, 1) while M1(t+2) runs.
 template <int FUN>
 __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_constant__ IcaParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -120,6 +126,8 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntiles = (p.n + kRows - 1) / kRows;
     if (p.state != nullptr && p.state[6] != 0.0) return;  // on-device convergence flag (uniform over the grid)
+    // tiles of this CTA: blockIdx.x, + gridDim.x, ...
+    const uint32_t T = (uint32_t)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kXStages; ++s) {
@@ -128,13 +136,18 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
         }
         mbar_init(ib(bars, B_WFULL), 1);
         mbar_init(ib(bars, B_A1), kRowWarps);
-        mbar_init(ib(bars, B_A2), kFeatWarps);
-        mbar_init(ib(bars, B_UFULL), 1);
-        mbar_init(ib(bars, B_UEMPTY), kRowWarps);
-        mbar_init(ib(bars, B_GREADY), kRowWarps);
-        mbar_init(ib(bars, B_TILEFREE), 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(ib(bars, B_UFULL + b), 1);
+            mbar_init(ib(bars, B_UEMPTY + b), kRowWarps);
+            mbar_init(ib(bars, B_GREADY + b), kRowWarps);
+            mbar_init(ib(bars, B_GFREE + b), 1);
+        }
+        for (int s = 0; s < kA2Slots; ++s) {
+            mbar_init(ib(bars, B_A2READY + s), 2);   // the two feature warps (features 0-31, 32-63) of a quarter tile
+            mbar_init(ib(bars, B_A2FREE + s), 1);
+        }
         mbar_init(ib(bars, B_HFULL), 1);
-        mbar_init(ib(bars, B_HEMPTY), kFeatWarps);
+        mbar_init(ib(bars, B_HEMPTY), kRowWarps / 2);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < kD; i += kThreadsIca) reinterpret_cast<float*>(bp + kOffMu)[i] = p.mu_pad[i];
@@ -153,10 +166,10 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
                 tma_load_2d(base + kOffW + (uint32_t)kb * kWTile, &p.map_whi, kb * 32, 0, ib(bars, B_WFULL));
                 tma_load_2d(base + kOffW + (uint32_t)(2 + kb) * kWTile, &p.map_wlo, kb * 32, 0, ib(bars, B_WFULL));
             }
-            uint32_t it = 0;
-            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int s = (int)(it % kXStages);
-                mbar_wait(ib(bars, B_XEMPTY + s), ((it / kXStages) & 1u) ^ 1u);
+            for (uint32_t it = 0; it < T; ++it) {
+                const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+                const int s = (int)(it & 1u);
+                mbar_wait(ib(bars, B_XEMPTY + s), ((it >> 1) & 1u) ^ 1u);
                 mbar_expect_tx(ib(bars, B_XFULL + s), kXStage);
                 tma_load_2d(base + kOffX + (uint32_t)s * kXStage, &p.map_x, 0, (int)(t * kRows), ib(bars, B_XFULL + s));
                 tma_load_2d(base + kOffX + (uint32_t)s * kXStage + 16384u, &p.map_x, 32, (int)(t * kRows), ib(bars, B_XFULL + s));
@@ -166,17 +179,14 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
         // ================================ MMA issuer ================================
         const uint32_t idesc = make_idesc_tf32(kNC, 0);
         mbar_wait(ib(bars, B_WFULL), 0);
-        uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const uint32_t ph = it & 1u;
-            const bool chain_start = (it % kFlushTiles) == 0;
-            const bool chain_end = ((it + 1) % kFlushTiles) == 0 || (t + gridDim.x >= ntiles);
-            // ---- MMA 1: U = A1 * W~^T
-            mbar_wait(ib(bars, B_A1), ph);
-            if (it > 0) mbar_wait(ib(bars, B_UEMPTY), (it - 1) & 1u);
+        auto issue_m1 = [&](uint32_t tau) {  // U[tau & 1] = A1 * W~^T
+            const int ub = (int)(tau & 1u);
+            mbar_wait(ib(bars, B_A1), tau & 1u);
+            if (tau >= 2) mbar_wait(ib(bars, B_UEMPTY + ub), ((tau >> 1) - 1u) & 1u);
             tc_fence_after();
-            if (lane == 0) ica_trace(p, 9, it);
+            if (lane == 0) ica_trace(p, 4, tau);
             if (elect_one()) {
+                const uint32_t acc = tmem_base + (uint32_t)(kAccU + 64 * ub);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t woff = (uint32_t)(ks >> 2) * kWTile + (uint32_t)(ks & 3) * 32u;
@@ -184,37 +194,49 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
                     const uint64_t dlo = make_desc_sw128(base + kOffW + 2u * kWTile + woff, 16u, 1024u);
                     const uint32_t a_hi = tmem_base + (uint32_t)(kA1 + ks * 8);
                     const uint32_t a_lo = a_hi + 64u;
-                    mma_tf32_ts(tmem_base + kAccU, a_lo, dhi, idesc, ks > 0 ? 1u : 0u);
-                    mma_tf32_ts(tmem_base + kAccU, a_hi, dlo, idesc, 1u);
-                    mma_tf32_ts(tmem_base + kAccU, a_hi, dhi, idesc, 1u);
+                    mma_tf32_ts(acc, a_lo, dhi, idesc, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
+                    mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
                 }
-                tc_commit(ib(bars, B_UFULL));
+                tc_commit(ib(bars, B_UFULL + ub));
             }
             __syncwarp();
-            if (lane == 0) ica_trace(p, 10, it);
-            // ---- MMA 2: H^T += A2 * G
-            mbar_wait(ib(bars, B_GREADY), ph);
-            mbar_wait(ib(bars, B_A2), ph);
-            if (chain_start && it > 0) mbar_wait(ib(bars, B_HEMPTY), ((it / kFlushTiles) - 1) & 1u);
-            tc_fence_after();
-            if (lane == 0) ica_trace(p, 11, it);
-            if (elect_one()) {
+        };
+        issue_m1(0);
+        for (uint32_t it = 0; it < T; ++it) {
+            if (it + 1 < T) issue_m1(it + 1);
+            // ---- M2(it): H^T = A2 * G[it & 1], quarter tile by quarter tile
+            const int gb = (int)(it & 1u);
+            mbar_wait(ib(bars, B_GREADY + gb), (it >> 1) & 1u);
+            if (it >= 1) mbar_wait(ib(bars, B_HEMPTY), (it - 1u) & 1u);
+            if (lane == 0) ica_trace(p, 5, it);
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t gran = 4u * it + (uint32_t)q;
+                const int slot = (int)(gran % 3u);
+                mbar_wait(ib(bars, B_A2READY + slot), (gran / 3u) & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t goff = kOffG + (uint32_t)gb * kGBuf + (uint32_t)q * kGTile;
 #pragma unroll
-                for (int ks = 0; ks < 16; ++ks) {
-                    const uint32_t goff = (uint32_t)(ks >> 2) * kGTile + (uint32_t)(ks & 3) * 32u;
-                    const uint64_t dhi = make_desc_sw128(base + kOffG + goff, 16u, 1024u);
-                    const uint64_t dlo = make_desc_sw128(base + kOffG + 4u * kGTile + goff, 16u, 1024u);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(kA2 + ks * 8);
-                    const uint32_t a_lo = a_hi + 128u;
-                    mma_tf32_ts(tmem_base + kAccH, a_lo, dhi, idesc, (chain_start && ks == 0) ? 0u : 1u);
-                    mma_tf32_ts(tmem_base + kAccH, a_hi, dlo, idesc, 1u);
-                    mma_tf32_ts(tmem_base + kAccH, a_hi, dhi, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t dhi = make_desc_sw128(base + goff + (uint32_t)ks * 32u, 16u, 1024u);
+                        const uint64_t dlo = make_desc_sw128(base + goff + 4u * kGTile + (uint32_t)ks * 32u, 16u, 1024u);
+                        const uint32_t a_hi = tmem_base + (uint32_t)(kA2 + 64 * slot + ks * 8);
+                        const uint32_t a_lo = a_hi + 32u;
+                        mma_tf32_ts(tmem_base + kAccH, a_lo, dhi, idesc, (q == 0 && ks == 0) ? 0u : 1u);
+                        mma_tf32_ts(tmem_base + kAccH, a_hi, dlo, idesc, 1u);
+                        mma_tf32_ts(tmem_base + kAccH, a_hi, dhi, idesc, 1u);
+                    }
+                    tc_commit(ib(bars, B_A2FREE + slot));
+                    if (q == 3) {
+                        tc_commit(ib(bars, B_GFREE + gb));
+                        tc_commit(ib(bars, B_HFULL));
+                    }
                 }
-                tc_commit(ib(bars, B_TILEFREE));
-                if (chain_end) tc_commit(ib(bars, B_HFULL));
+                __syncwarp();
             }
-            __syncwarp();
-            if (lane == 0) ica_trace(p, 12, it);
+            if (lane == 0) ica_trace(p, 6, it);
         }
     } else if (warp < kRowWarps) {
         // ================================ row warps ================================
@@ -222,88 +244,116 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
         const int r = q * 32 + lane;                      // row inside the tile = TMEM lane
         const uint32_t lane_field = (uint32_t)(q * 32) << 16;
         const bool tr = (warp == 0 && lane == 0);
-        float acc[16];
+        const bool h_owner = (q < 2);                     // lanes 0-63 of H = features: these warps drain H
+        float acc[16], hacc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 16; ++j) {
+            acc[j] = 0.f;
+            hacc[j] = 0.f;
+        }
         int nvalid = 0;
-        uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int s = (int)(it % kXStages);
-            const uint32_t ph = it & 1u;
+        // x - mu of this thread's row (features 16 cq ..) -> A1 hi / lo, for the tile in X stage `it`
+        auto transform_a = [&](uint32_t it) {
+            const int64_t t = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int s = (int)(it & 1u);
             const bool valid = t * kRows + r < p.n;
             nvalid += valid ? 1 : 0;
-            // ---- transform-A: this thread's row, features 16*cq .. 16*cq+15
-            mbar_wait(ib(bars, B_XFULL + s), (it / kXStages) & 1u);
-            if (tr) ica_trace(p, 0, it);
+            if (tr) ica_trace(p, 7, it);
+            mbar_wait(ib(bars, B_XFULL + s), (it >> 1) & 1u);
+            if (tr) ica_trace(p, 8, it);
             uint32_t v[16];
-            {
-                const uint8_t* xr = bp + kOffX + (uint32_t)s * kXStage + (uint32_t)(cq >> 1) * 16384u + r * 128;
+            const uint8_t* xr = bp + kOffX + (uint32_t)s * kXStage + (uint32_t)(cq >> 1) * 16384u + r * 128;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                    const int c = (cq & 1) * 4 + c4;
-                    const float4 x4 = *reinterpret_cast<const float4*>(xr + ((c ^ (r & 7)) << 4));
-                    const float4 m4 = *reinterpret_cast<const float4*>(mus + cq * 16 + c4 * 4);
-                    v[c4 * 4 + 0] = __float_as_uint(valid ? x4.x - m4.x : 0.f);
-                    v[c4 * 4 + 1] = __float_as_uint(valid ? x4.y - m4.y : 0.f);
-                    v[c4 * 4 + 2] = __float_as_uint(valid ? x4.z - m4.z : 0.f);
-                    v[c4 * 4 + 3] = __float_as_uint(valid ? x4.w - m4.w : 0.f);
-                }
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int c = (cq & 1) * 4 + c4;
+                const float4 x4 = *reinterpret_cast<const float4*>(xr + ((c ^ (r & 7)) << 4));
+                const float4 m4 = *reinterpret_cast<const float4*>(mus + cq * 16 + c4 * 4);
+                v[c4 * 4 + 0] = __float_as_uint(valid ? x4.x - m4.x : 0.f);
+                v[c4 * 4 + 1] = __float_as_uint(valid ? x4.y - m4.y : 0.f);
+                v[c4 * 4 + 2] = __float_as_uint(valid ? x4.z - m4.z : 0.f);
+                v[c4 * 4 + 3] = __float_as_uint(valid ? x4.w - m4.w : 0.f);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(ib(bars, B_XEMPTY + s));
-            // A1 is free: MMA 1 of the previous tile completed before this warp passed u_full(t-1)
-            {
-                const uint32_t a = tmem_base + lane_field + (uint32_t)(kA1 + cq * 16);
-                tmem_st16(a, v);
+            // A1 is free: M1 of the previous tile has completed (this warp has seen its u_full)
+            const uint32_t a = tmem_base + lane_field + (uint32_t)(kA1 + cq * 16);
+            tmem_st16(a, v);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float f = __uint_as_float(v[k]);
-                    v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
-                }
-                tmem_st16(a + 64u, v);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ib(bars, B_A1));
-            }
-            if (tr) ica_trace(p, 1, it);
-            // ---- epilogue-1: U[r][16*cq ..] -> g
-            mbar_wait(ib(bars, B_UFULL), ph);
+            for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) - __uint_as_float(v[k] & 0xFFFFE000u));
+            tmem_st16(a + 64u, v);
+            if (tr) ica_trace(p, 9, it);
+            tmem_st_wait();
+            if (tr) ica_trace(p, 10, it);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ib(bars, B_A1));
+        };
+        auto drain_h = [&](uint32_t tau) {  // H of tile tau -> registers
+            mbar_wait(ib(bars, B_HFULL), tau & 1u);
             tc_fence_after();
-            if (tr) ica_trace(p, 2, it);
-            {
-                tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccU + cq * 16), v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ib(bars, B_UEMPTY));
-            }
+            uint32_t w[16];
+            tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccH + cq * 16), w);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(ica_g_acc<FUN>(__uint_as_float(v[j]), acc[j]));
-            if (tr) ica_trace(p, 3, it);
-            // G tiles are free once MMA 2 of the previous tile has completed
-            if (it > 0) mbar_wait(ib(bars, B_TILEFREE), (it - 1) & 1u);
-            if (tr) ica_trace(p, 4, it);
+            for (int j = 0; j < 16; ++j) hacc[j] += __uint_as_float(w[j]);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ib(bars, B_HEMPTY));
+        };
+        transform_a(0);
+        for (uint32_t it = 0; it < T; ++it) {
+            const int ub = (int)(it & 1u);
+            if (h_owner && it >= 2) drain_h(it - 2);  // M2(it-2) precedes M1(it) on the tensor pipe
+            // ---- epilogue-1: U[r][16*cq ..] -> g
+            mbar_wait(ib(bars, B_UFULL + ub), (it >> 1) & 1u);
+            tc_fence_after();
+            if (tr) ica_trace(p, 0, it);
+            uint32_t u[16];
+            tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccU + 64 * ub + cq * 16), u);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ib(bars, B_UEMPTY + ub));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) u[j] = __float_as_uint(ica_g_acc<FUN>(__uint_as_float(u[j]), acc[j]));
+            if (tr) ica_trace(p, 1, it);
+            // ---- A operand of the next tile's M1 (issued before M2(it), so it overlaps the G store below)
+            if (it + 1 < T) transform_a(it + 1);
+            if (tr) ica_trace(p, 2, it);
+            // ---- G[it & 1]: free once M2(it-2) has completed
+            if (it >= 2) mbar_wait(ib(bars, B_GFREE + ub), ((it >> 1) - 1u) & 1u);
             {
                 // K-major operand tiles [comp][32 rows] per 32-row block (= q), SWIZZLE_128B
-                uint8_t* gh = bp + kOffG + (uint32_t)q * kGTile + (lane & 3) * 4;
+                uint8_t* gh = bp + kOffG + (uint32_t)ub * kGBuf + (uint32_t)q * kGTile + (lane & 3) * 4;
                 const int rc = lane >> 2;  // 16 B chunk of this row inside the 128 B line
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int c = cq * 16 + j;
                     const int off = c * 128 + ((rc ^ (j & 7)) << 4);   // (c & 7) == (j & 7)
-                    const float g = __uint_as_float(v[j]);
+                    const float g = __uint_as_float(u[j]);
                     *reinterpret_cast<float*>(gh + off) = g;
-                    *reinterpret_cast<float*>(gh + 4u * kGTile + off) = g - __uint_as_float(v[j] & 0xFFFFE000u);
+                    *reinterpret_cast<float*>(gh + 4u * kGTile + off) = g - __uint_as_float(u[j] & 0xFFFFE000u);
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ib(bars, B_GREADY));
+                if (lane == 0) mbar_arrive(ib(bars, B_GREADY + ub));
             }
-            if (tr) ica_trace(p, 5, it);
+            if (tr) ica_trace(p, 3, it);
+        }
+        if (h_owner) {
+            if (T >= 2) drain_h(T - 2);
+            drain_h(T - 1);
+            const int f = q * 32 + lane;
+            if (f < p.d) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = cq * 16 + j;
+                    if (c < p.nc) atomicAdd(&p.Ht[(size_t)f * p.nc + c], (double)hacc[j]);
+                }
+            }
         }
         // per-column totals of this warp's rows -> sum of g' -> one atomic per column per warp
-        const float fvalid = (float)nvalid, finvalid = (float)((int)it - nvalid);
+        const float fvalid = (float)nvalid, finvalid = (float)((int)T - nvalid);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             float sgp = acc[j];
@@ -314,76 +364,46 @@ __global__ void __launch_bounds__(kThreadsIca, 1) ica_fused_kernel(const __grid_
             const int c = cq * 16 + j;
             if (lane == 0 && c < p.nc) atomicAdd(&p.gp[c], (double)sgp);
         }
-    } else if ((warp & 3) < 2) {
+    } else if ((warp & 3) < 2 && warp < 22) {
         // ================================ feature warps ================================
         const int q = warp & 3;                      // 0, 1: features 0-31, 32-63
-        const int rq = (warp - kRowWarps) >> 2;      // rows 32*rq .. 32*rq+31 of the tile; H columns 16*rq .. +15
+        const int rh = (warp - kRowWarps) >> 2;      // quarter tiles rh and rh + 2
         const int f = q * 32 + lane;
         const uint32_t lane_field = (uint32_t)(q * 32) << 16;
         const float mu_f = mus[f];
-        const bool tr = (warp == kRowWarps && lane == 0);
-        float racc[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) racc[j] = 0.f;
-        uint32_t it = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-            const int s = (int)(it % kXStages);
-            mbar_wait(ib(bars, B_XFULL + s), (it / kXStages) & 1u);
-            if (tr) ica_trace(p, 6, it);
+        for (uint32_t it = 0; it < T; ++it) {
+            const int s = (int)(it & 1u);
+            mbar_wait(ib(bars, B_XFULL + s), (it >> 1) & 1u);
             const uint8_t* xs = bp + kOffX + (uint32_t)s * kXStage + (uint32_t)(f >> 5) * 16384u + (f & 3) * 4;
             const int fc = (f & 31) >> 2;
-            uint32_t v0[16], v1[16];
+            // both quarter tiles into registers, then the X stage can be recycled
+            uint32_t va[32], vb[32];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int row = rq * 32 + k;
-                v0[k] = __float_as_uint(*reinterpret_cast<const float*>(xs + row * 128 + ((fc ^ (row & 7)) << 4)) - mu_f);
-            }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const int row = rq * 32 + 16 + k;
-                v1[k] = __float_as_uint(*reinterpret_cast<const float*>(xs + row * 128 + ((fc ^ (row & 7)) << 4)) - mu_f);
+            for (int k = 0; k < 32; ++k) {
+                const int ra = rh * 32 + k, rb = (rh + 2) * 32 + k;
+                va[k] = __float_as_uint(*reinterpret_cast<const float*>(xs + ra * 128 + ((fc ^ (ra & 7)) << 4)) - mu_f);
+                vb[k] = __float_as_uint(*reinterpret_cast<const float*>(xs + rb * 128 + ((fc ^ (rb & 7)) << 4)) - mu_f);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(ib(bars, B_XEMPTY + s));
-            // A2 is free once MMA 2 of the previous tile has completed
-            if (it > 0) mbar_wait(ib(bars, B_TILEFREE), (it - 1) & 1u);
-            tc_fence_after();
-            if (tr) ica_trace(p, 7, it);
-            const uint32_t a = tmem_base + lane_field + (uint32_t)(kA2 + rq * 32);
-            tmem_st16(a, v0);
-            tmem_st16(a + 16u, v1);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                v0[k] = __float_as_uint(__uint_as_float(v0[k]) - __uint_as_float(v0[k] & 0xFFFFE000u));
-                v1[k] = __float_as_uint(__uint_as_float(v1[k]) - __uint_as_float(v1[k] & 0xFFFFE000u));
-            }
-            tmem_st16(a + 128u, v0);
-            tmem_st16(a + 144u, v1);
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ib(bars, B_A2));
-            if (tr) ica_trace(p, 8, it);
-            // ---- H flush: every feature warp reads out its 16 columns
-            const bool chain_end = ((it + 1) % kFlushTiles) == 0 || (t + gridDim.x >= ntiles);
-            if (chain_end) {
-                mbar_wait(ib(bars, B_HFULL), (it / kFlushTiles) & 1u);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t* v = h ? vb : va;
+                const uint32_t gran = 4u * it + (uint32_t)(rh + 2 * h);
+                const int slot = (int)(gran % 3u);
+                mbar_wait(ib(bars, B_A2FREE + slot), ((gran / 3u) & 1u) ^ 1u);
                 tc_fence_after();
-                uint32_t w[16];
-                tmem_ld16(tmem_base + lane_field + (uint32_t)(kAccH + rq * 16), w);
-                tmem_ld_wait();
+                const uint32_t a = tmem_base + lane_field + (uint32_t)(kA2 + 64 * slot);
+                tmem_st16(a, v);
+                tmem_st16(a + 16u, v + 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) racc[j] += __uint_as_float(w[j]);
+                for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) - __uint_as_float(v[k] & 0xFFFFE000u));
+                tmem_st16(a + 32u, v);
+                tmem_st16(a + 48u, v + 16);
+                tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(ib(bars, B_HEMPTY));
-            }
-        }
-        if (f < p.d) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int c = rq * 16 + j;
-                if (c < p.nc) atomicAdd(&p.Ht[(size_t)f * p.nc + c], (double)racc[j]);
+                if (lane == 0) mbar_arrive(ib(bars, B_A2READY + slot));
             }
         }
     }
@@ -468,11 +488,12 @@ struct IcaFused {
                     return sacc / (b - a);
                 };
                 fprintf(stderr,
-                        "[ica trace] period %.0f | row: xfull->a1 %.0f  a1->ufull %.0f  ufull->g %.0f  g->tilefree %.0f  tilefree->gready %.0f  "
-                        "gready->next xfull %.0f | feat: xfull->tilefree %.0f  tilefree->a2 %.0f | mma: a1got->m1 issued %.0f  m1->g/a2 got %.0f  "
-                        "->m2 issued %.0f  m2->next a1 got %.0f\n",
-                        mean(0, 0, 1), mean(1, 0, 0), mean(2, 1, 0), mean(3, 2, 0), mean(4, 3, 0), mean(5, 4, 0), mean(0, 5, 1),
-                        mean(7, 6, 0), mean(8, 7, 0), mean(10, 9, 0), mean(11, 10, 0), mean(12, 11, 0), mean(9, 12, 1));
+                        "[ica trace] period %.0f | row: ufull->tanh done %.0f  ->trA(next) done %.0f  ->G stored %.0f  ->next ufull %.0f | "
+                        "mma: M1 start->M2 start %.0f  M2 start->issued %.0f  M2 issued->next M1 start %.0f\n",
+                        mean(0, 0, 1), mean(1, 0, 0), mean(2, 1, 0), mean(3, 2, 0), mean(0, 3, 1), mean(5, 4, 0), mean(6, 5, 0),
+                        mean(4, 6, 1));
+                fprintf(stderr, "[ica trace]   trA: wait X %.0f  read+st issue %.0f  st wait %.0f\n", mean(8, 7, 0), mean(9, 8, 0),
+                        mean(10, 9, 0));
             }
         }
     }
