@@ -491,7 +491,7 @@ def test_tc_atb_precise_vs_long_chains(pd, monkeypatch):
 
 
 @pytest.mark.parametrize("fun", [0, 1, 2])  # logcosh, exp, cube
-@pytest.mark.parametrize("n,d", [(50_000, 12), (40_001, 64)])
+@pytest.mark.parametrize("n,d", [(5_000, 8), (20_000, 64), (50_000, 12), (40_001, 64)])  # 1, 2, 3 tiles per CTA; ragged last tile
 def test_fastica_one_pass_kernel_matches_three_kernel_path(pd, monkeypatch, fun, n, d):
     """The fused tcgen05 pass (U, g(U), sum g', H^T in one read of X) against tc_xb + nonlin + tc_atb."""
     x, _ = synth.mixed_sources(n, d, seed=d + fun, dtype=np.float32)
