@@ -393,12 +393,18 @@ def main():
             achieved = v["work"] / (v["total_ms"] * 1e-3) / 1e9
             traffic = None
             try:
+                # ncu's DRAM bytes were captured on the c2 shape with fewer rows: what carries over to this
+                # launch is the measured traffic / algorithmic ratio (profiles/roofline_traffic.json)
                 tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-                traffic = tj.get(top, {}).get("dram_bytes_per_launch")
+                ratio = tj.get(top, {}).get("ratio")
+                if ratio is not None:
+                    traffic = float(ratio) * v["work"] / v["count"]
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
+                    "frac": achieved / hbm_peak, "traffic": traffic,
+                    "traffic_source": "ncu dram bytes / algorithmic bytes ratio (profiles/roofline_traffic.json) x this launch's algorithmic bytes",
+                    "peak_source": peak_kind,
                     "launches": v["count"], "avg_ms": v["total_ms"] / v["count"],
                     "algorithmic_bytes_per_launch": v["work"] / v["count"],
                     "kernel_share_of_step": v["total_ms"] / dev_ms,
