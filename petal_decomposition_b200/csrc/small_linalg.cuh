@@ -51,8 +51,9 @@ __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, doubl
                                                 double& c, double& s, double* t_out = nullptr) {
     const double na = sqrt(alpha), nb = sqrt(beta);
     if (!(fabs(gamma) > tol * na * nb + noise * (na + nb))) return false;  // also false for NaN/zero rows
-    double zeta = (beta - alpha) / (2.0 * gamma);
-    double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    // (an f32 tangent with f64 normalisation was tried: same step time - the step is not bound by this chain)
+    const double zeta = (beta - alpha) / (2.0 * gamma);
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     c = rsqrt(1.0 + t * t);
     s = c * t;
     if (t_out) *t_out = t;
@@ -107,7 +108,7 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
     const unsigned gmask = 0xFFFFu << (lane & 16);
     for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
         // squared row norms: recomputed exactly once per sweep, then carried through the rotations
-        // (|a'|^2 = |a|^2 - t g, |b'|^2 = |b|^2 + t g), so a step needs one inner product instead of three
+        // (|a'|^2 = c^2 |a|^2 - 2 c s g + s^2 |b|^2, ...), so a step needs one inner product instead of three
         for (int j = warp; j < m; j += nwarps) {
             double a = 0.0;
             for (int e = lane; e < len; e += 32) a += M[(size_t)j * len + e] * M[(size_t)j * len + e];
@@ -129,9 +130,9 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
                 double c, s, t;
                 if (!jacobi_rotation(al, be, ga, tol, noise, c, s, &t)) continue;
                 __syncwarp(gmask);  // every lane of the group has read nrm[p], nrm[q]
-                if (gl == 0) {
-                    nrm[p] = fmax(al - t * ga, 0.0);
-                    nrm[q] = be + t * ga;
+                if (gl == 0) {  // exact for any rotation (c, s)
+                    nrm[p] = fmax(c * c * al - 2.0 * c * s * ga + s * s * be, 0.0);
+                    nrm[q] = fmax(s * s * al + 2.0 * c * s * ga + c * c * be, 0.0);
                 }
                 for (int e = gl; e < len; e += 16) {
                     double x = mp[e], y = mq[e];
@@ -327,8 +328,8 @@ jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
                 if (!jacobi_rotation(al, be, ga, tol, noise, c, s, &t)) continue;  // block-uniform
                 __syncthreads();
                 if (tid == 0) {
-                    nrm2[p] = fmax(al - t * ga, 0.0);
-                    nrm2[q] = be + t * ga;
+                    nrm2[p] = fmax(c * c * al - 2.0 * c * s * ga + s * s * be, 0.0);  // exact for any rotation (c, s)
+                    nrm2[q] = fmax(s * s * al + 2.0 * c * s * ga + c * c * be, 0.0);
                     rot[sweep] = 1;
                 }
                 for (int e = tid; e < len; e += 256) {
@@ -435,9 +436,21 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
                                             200 * 1024));
             attr_set = true;
         }
+        DBuf<int> info;
+        const bool want_info = getenv("PETAL_JACOBI_INFO") != nullptr;
+        if (want_info) {
+            info.alloc(ctx, 1);
+            info.zero();
+        }
         jacobi_smem_kernel<<<1, kJacobiSmemThreads, smem, ctx->stream>>>(A, (int)m, (int)len, Aout, Jt, sig,
-                                                                         max_sweeps, tol, input_noise_rel, run_flag, nullptr);
+                                                                         max_sweeps, tol, input_noise_rel, run_flag, info.p);
         check_launch(ctx);
+        if (want_info) {
+            int h = 0;
+            PETAL_CUDA(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            fprintf(stderr, "[jacobi_smem] m %d len %d sweeps %d\n", (int)m, (int)len, h);
+        }
         return -1;
     }
     DBuf<double> M(ctx, (size_t)(m * len));
