@@ -277,7 +277,7 @@ def test_pca_no_centering_vs_oracle(pd):
 
 # ------------------------------------------------------------ randomized PCA vs oracle
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-4)])
-@pytest.mark.parametrize("n,d,k,q", [(20000, 256, 16, 4), (3000, 75, 8, 7)])
+@pytest.mark.parametrize("n,d,k,q", [(20000, 256, 16, 4), (3000, 75, 8, 7), (2, 5, 1, 2), (40, 300, 5, 3)])
 def test_rpca_vs_oracle(pd, dtype, tol, n, d, k, q):
     x = synth.lowrank_noise(n, d, rank=min(d, 40), decay=0.8, noise=0.01, seed=11, dtype=dtype)
     omega = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(d, k + 10, dtype)
@@ -298,6 +298,21 @@ def test_rpca_vs_oracle(pd, dtype, tol, n, d, k, q):
     m.fit(x)
     assert m.rng.state() != s1
     assert rel(m.singular_values(), ref.singular_values()) < max(tol, 1e-6)
+
+
+def test_rpca_f32_wide_sketch(pd):
+    """k + 10 > 80 columns: the X^T Y kernel has no room for its chain-cutting accumulator buffers there and runs
+    the long-chain mode; singular values must still be inside the f32 tolerance on a well-separated spectrum."""
+    n, d, k, q = 30_011, 512, 100, 2
+    x = synth.lowrank_noise(n, d, rank=300, decay=0.97, noise=1e-3, seed=4, dtype=np.float32)
+    omega = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(d, k + 10, np.float32)
+    ref = opca.RandomizedPca(k, n_iter=q)
+    ref.fit(x.astype(np.float64), omega.astype(np.float64))
+    m = pd.RandomizedPcaBuilder.new(k).seed(RNG_SEED).n_power_iter(q).build()
+    m.fit(x)
+    assert rel(m.singular_values(), ref.singular_values()) < 1e-4
+    assert rel(m.explained_variance_ratio(), ref.explained_variance_ratio()) < 1e-4
+    assert opca.principal_angles(m.components()[:50], ref.components[:50]).max() < 5e-3
 
 
 def test_rpca_f32_noise_floor_accuracy(pd):
