@@ -434,7 +434,10 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     }
     const int64_t nblk = ceil_div(n, 32);
     DBuf<T> Y(ctx, panel ? (size_t)(nblk * ly * 32) : (size_t)(n * ly));
-    DBuf<T> Ylo(ctx, panel ? (size_t)(nblk * ly * 32) : 0);  // y - tf32(y), panel-major: B_lo operand of the X^T Y passes
+    // y - tf32(y), the B_lo operand of the X^T Y passes, is derived inside tc_atb by default; PETAL_YLO=1 keeps the
+    // older second panel in HBM (written by tc_xb, TMA-loaded by tc_atb) for comparison
+    const bool ylo_panel = panel && getenv("PETAL_YLO") != nullptr && atoi(getenv("PETAL_YLO")) != 0;
+    DBuf<T> Ylo(ctx, ylo_panel ? (size_t)(nblk * ly * 32) : 0);
     DBuf<double> small(ctx, (size_t)(l * l + d * l + 1));  // [Gram of Y | C' | tv] reduced together
     double* G2 = small.p;
     double* Cp = small.p + l * l;

@@ -269,7 +269,6 @@ jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
                    int* __restrict__ info) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double red[8];
-    __shared__ double bc[3];
     unsigned target = 0;
     auto row_norm2 = [&](int j) {  // block-wide, result in bc[0] for every thread after the sync
         double a = 0.0;
@@ -351,7 +350,6 @@ jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
         if (reinterpret_cast<volatile int*>(rot)[sweep] == 0) break;  // written before the last barrier of the sweep: same value in every CTA
     }
     if (blockIdx.x == 0 && tid == 0 && info) info[0] = sweeps;
-    (void)bc;
 }
 
 __global__ void __launch_bounds__(256)

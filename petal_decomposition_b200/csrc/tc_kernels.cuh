@@ -27,7 +27,8 @@ namespace tc {
 
 constexpr int kTransformWarps = 16;          // two warps per 32 TMEM lanes: each owns one half (16 values) of a K block
 constexpr int kEpilogueWarps = 8;            // tc_atb: only the first half keeps the register accumulators
-constexpr int kThreads = (kTransformWarps + 4) * 32;  // + TMA, MMA, TMEM-alloc, spare
+constexpr int kThreads = (kTransformWarps + 4) * 32;  // + X TMA, 2 x MMA, B TMA (+ TMEM alloc); a 21st warp would round
+                                                       // the register file split up to 24 warps (80 regs per thread)
 constexpr int kMT = 2;            // M tiles (128 TMEM lanes each) per CTA
 constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
 constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
@@ -73,6 +74,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             __trap();
         }
     }
+}
+// non-blocking probe of a barrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 // true in exactly one (elected) lane of a fully converged warp; keeps the surrounding code warp-uniform so
 // that descriptors / addresses live in uniform registers (the tensor-core issue path reads those)
@@ -195,6 +208,8 @@ struct TcParams {
     int64_t ldy;
     int y_vec;            // Y rows may be written with 16 B stores
     int y_panel;          // tc_xb: write Y panel-major [row block of 32][n_pad][32]; tc_atb: B operand is panel-major
+    int b_split;          // tc_atb, panel-major Y: only the Y panel is loaded; a splitter warp derives the y - tf32(y)
+                          // operand tile in shared memory (no Y_lo panel in HBM)
     double* sumsq;        // nullable
     // tc_atb outputs / decomposition
     double* Z;            // [da x ldz] f64, atomically accumulated
@@ -258,6 +273,7 @@ __device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return ba
 __device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, int b) { return base + 8u * (40 + (uint32_t)b); }   // 40 .. 42
 __device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base, int b) { return base + 8u * (47 + (uint32_t)b); }  // 47 .. 49
 __device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (44 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_full_b2(uint32_t base, int s) { return base + 8u * (50 + (uint32_t)s); }  // B ring, after the splitter
 
 // ------------------------------------------------------------------------------------------
 // the kernel (ATB = false: tc_xb, ATB = true: tc_atb; NP = compile-time n_pad for tc_atb)
@@ -338,7 +354,6 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                                                int S) {
     {
         const int half = warp >> 3;
-        constexpr bool epi = true;  // every transform warp also runs the epilogue
         const int mt = (warp >> 2) & 1;
         const int q = warp & 3;
         const int lrow = q * 32 + lane;           // lane (= row / feature) inside the M tile
@@ -405,7 +420,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                     for (int jj = 0; jj < 16; ++jj) {
                         const float y = valid ? __uint_as_float(w[jj]) : 0.f;
                         yb[(c0 + jj) * 32] = y;
-                        yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
+                        if (p.Ylo != nullptr) yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
                     }
                 }
             } else {
@@ -528,7 +543,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
             for (int jj = 0; jj < 16; ++jj) {
                 const float y = valid ? w[jj] : 0.f;
                 yb[(c0 + jj) * 32] = y;
-                yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
+                if (p.Ylo != nullptr) yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
             }
         };
         auto store_rowmajor_chunk = [&](int64_t row0, int c0, const float* w) {
@@ -833,6 +848,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
         for (int s = 0; s < SB; ++s) {
             mbar_init(bar_full_b(bars, s), 1);
+            mbar_init(bar_full_b2(bars, s), 1);
             // released by the two MMA warps, or by the transform warps when they consume the raw row-major Y tile
             mbar_init(bar_empty_b(bars, s), (ATB && !panel) ? kTransformWarps : kMT);
         }
@@ -855,7 +871,86 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L.tmem_slot);
 
     if (warp >= kTransformWarps) {
-        if (warp == kTransformWarps) {
+        if (ATB && panel && p.b_split && (warp == kTransformWarps || warp == kTransformWarps + 3)) {
+            // ================ tc_atb with in-kernel B_lo: one TMA producer for both rings + a splitter warp ================
+            // Only the Y panel is in HBM.  The rows of a CTA's slice are contiguous, so K block i of the CTA starts at
+            // row s0 + 32 i whatever the group structure.
+            const int fg = (int)(blockIdx.x % (unsigned)p.fgroups);
+            const int64_t s0 = (int64_t)(blockIdx.x / (unsigned)p.fgroups) * p.slice_rows;
+            const int64_t s1 = min(p.n, s0 + p.slice_rows);
+            const uint32_t total = (s1 > s0) ? (uint32_t)((s1 - s0 + kKB - 1) / kKB) : 0u;
+            if (warp == kTransformWarps) {
+                // lane 0 feeds the X ring and the B ring, whichever has a free stage (non-blocking probes: the two
+                // rings are released by different consumers and must not wait for each other)
+                if (lane == 0) {
+                    uint32_t ix = 0, ib = 0, idle = 0;
+                    while (ix < total || ib < total) {
+                        bool progressed = false;
+                        if (ix < total) {
+                            const int sx = (int)(ix % (uint32_t)S);
+                            if (mbar_test(bar_empty_x(bars, sx), ((ix / (uint32_t)S) & 1u) ^ 1u)) {
+                                const uint32_t full = bar_full(bars, sx);
+                                mbar_expect_tx(full, L.stage_x);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    tma_load_2d(base + L.x + (uint32_t)sx * L.stage_x + (uint32_t)j * 4096u, &p.map_x,
+                                                fg * 256 + 32 * j, (int)(s0 + (int64_t)ix * kKB), full);
+                                ++ix;
+                                progressed = true;
+                            }
+                        }
+                        if (ib < total) {
+                            const int sb = (int)(ib % (uint32_t)SB);
+                            if (mbar_test(bar_empty_b(bars, sb), ((ib / (uint32_t)SB) & 1u) ^ 1u)) {
+                                const uint32_t fullb = bar_full_b(bars, sb);
+                                const int64_t r = s0 + (int64_t)ib * kKB;
+                                mbar_expect_tx(fullb, L.stage_b);
+                                tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, 0, (int)(r / 32) * n_pad, fullb);
+                                ++ib;
+                                progressed = true;
+                            }
+                        }
+                        if (progressed) {
+                            idle = 0;
+                        } else if (++idle > 400000000u) {
+                            printf("petal tc kernel: TMA producer stalled (block %d)\n", blockIdx.x);
+                            __trap();
+                        }
+                    }
+                }
+            } else {
+                // splitter: the block TMA dropped into the B ring is the B_hi operand as it is (the tensor core ignores
+                // the low mantissa bits); B_lo = y - tf32(y) is derived here, element-wise in the same swizzled layout
+                for (uint32_t it = 0; it < total; ++it) {
+                    const int sb = (int)(it % (uint32_t)SB);
+                    mbar_wait(bar_full_b(bars, sb), (it / (uint32_t)SB) & 1u);
+                    const float4* bh = reinterpret_cast<const float4*>(base_ptr + L.bhi + (uint32_t)sb * L.stage_b);
+                    float4* bl = reinterpret_cast<float4*>(base_ptr + L.blo + (uint32_t)sb * L.stage_b);
+                    constexpr int kPer = ATB ? (NP * 8 + 31) / 32 : 1;  // 16 B chunks per lane
+                    float4 h[kPer];
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = lane + 32 * u;
+                        if (e < NP * 8) h[u] = bh[e];
+                    }
+#pragma unroll
+                    for (int u = 0; u < kPer; ++u) {
+                        const int e = lane + 32 * u;
+                        if (e < NP * 8) {
+                            float4 l4;
+                            l4.x = h[u].x - __uint_as_float(__float_as_uint(h[u].x) & 0xFFFFE000u);
+                            l4.y = h[u].y - __uint_as_float(__float_as_uint(h[u].y) & 0xFFFFE000u);
+                            l4.z = h[u].z - __uint_as_float(__float_as_uint(h[u].z) & 0xFFFFE000u);
+                            l4.w = h[u].w - __uint_as_float(__float_as_uint(h[u].w) & 0xFFFFE000u);
+                            bl[e] = l4;
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_full_b2(bars, sb));
+                }
+            }
+        } else if (warp == kTransformWarps) {
             // ================================ TMA producer: X ring ================================
             if (lane == 0) {
                 uint32_t it = 0;
@@ -899,9 +994,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             // panel-major Y: rows (r/32)*n_pad .. +n_pad of the [blocks*n_pad][32] views are exactly
                             // the K-major Y_hi / Y_lo operand tiles
                             const int r = (int)(g.row0 + kb * kKB);
-                            mbar_expect_tx(fullb, 2u * L.stage_b);
+                            mbar_expect_tx(fullb, p.b_split ? L.stage_b : 2u * L.stage_b);
                             tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, 0, (r / 32) * n_pad, fullb);
-                            tma_load_2d(base + L.blo + (uint32_t)sb * L.stage_b, &p.map_blo, 0, (r / 32) * n_pad, fullb);
+                            if (!p.b_split)
+                                tma_load_2d(base + L.blo + (uint32_t)sb * L.stage_b, &p.map_blo, 0, (r / 32) * n_pad, fullb);
                         } else if (ATB) {
                             // row-major Y: box {n_pad, 32 rows}, transposed + split by the transform warps
                             mbar_expect_tx(fullb, L.stage_b);
@@ -963,7 +1059,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const uint32_t phb = (it / (uint32_t)SB) & 1u;
                     // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are TMA-loaded panels, or
                     // (row-major Y) produced by ALL transform warps - then both halves must have checked in first
-                    if (!ATB || panel) mbar_wait(bar_full_b(bars, sb), phb);
+                    if (!ATB || panel) mbar_wait((ATB && p.b_split) ? bar_full_b2(bars, sb) : bar_full_b(bars, sb), phb);
                     // (tc_xb also checks both halves in first: measured faster than issuing per half there)
                     constexpr bool kSplitIssue = ATB && panel;
                     if (!kSplitIssue) {
@@ -1206,7 +1302,9 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.map_x = make_map_2d(A, (uint64_t)da, (uint64_t)n, (uint64_t)lda, 32, 32, true);
     if (b_panel) {
         p.map_bhi = make_map_2d(B, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
-        p.map_blo = make_map_2d(B_lo_panel, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
+        p.b_split = (B_lo_panel == nullptr) ? 1 : 0;  // no Y_lo panel: the operand tile is derived inside the kernel
+        p.map_blo = p.b_split ? p.map_bhi
+                              : make_map_2d(B_lo_panel, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
     } else {
         p.map_bhi = make_map_2d(B, (uint64_t)db, (uint64_t)n, (uint64_t)ldb, (uint32_t)n_pad, 32, false);
         p.map_blo = p.map_bhi;
