@@ -751,7 +751,8 @@ inline void launch_panel_gram(petal_ctx* ctx, const float* Yp, int64_t n, int np
 
 // out[r][j] = sum_c Y[r][c] * S[c][j]; CTAs loop over pairs of row blocks (64 rows); S staged once in shared
 // memory (l x kp floats, kp = k rounded up to 32*KV).  256 threads = 8 (row groups) x 32 (column groups): each thread
-// owns rows i0 + 8u (u < 8) and the KV contiguous columns KV*j0 ... (one vector load of S per c).
+// owns the 8 consecutive rows 8 i0 .. 8 i0 + 7 (two broadcast LDS.128 per c) and the KV contiguous columns KV*j0 ...
+// (one vector load of S per c).
 template <int KV>
 __global__ void __launch_bounds__(256)
 panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const float* __restrict__ S, int k,
@@ -759,7 +760,8 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
     extern __shared__ float psm[];
     constexpr int KP = 32 * KV;
     float* Ss = psm;                   // [l][KP]
-    float* Ts = psm + (size_t)l * KP;  // [np][65]: column c of the 64 rows at c*65 + i
+    constexpr int TS = 68;             // 64 rows + pad, 16 B aligned rows
+    float* Ts = psm + (size_t)l * KP;  // [np][TS]: column c of the 64 rows at c*TS + i
     const int tid = threadIdx.x;
     for (int e = tid; e < l * KP; e += 256) {
         const int c = e / KP, j = e % KP;
@@ -770,12 +772,15 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
     const int i0 = tid >> 5, j0 = tid & 31;
     // per column (max |score|, first row, sign) over the rows this thread produces: the u-based sign flip
     // (reference src/pca.rs:815-850) needs it, and taking it here saves re-reading the scores
-    AbsMax best[KV];
+    // (kept in fp32 - the scores are fp32 - and widened at the end: f64 compares per element would cost as much as
+    // the product itself)
+    float best_a[KV], best_s[KV];
+    int64_t best_i[KV];
 #pragma unroll
     for (int v = 0; v < KV; ++v) {
-        best[v].a = -1.0;
-        best[v].sgn = 1.0;
-        best[v].idx = INT64_MAX;
+        best_a[v] = -1.f;
+        best_s[v] = 1.f;
+        best_i[v] = INT64_MAX;
     }
     for (int64_t pb = blockIdx.x; pb < npairs; pb += gridDim.x) {
         __syncthreads();
@@ -783,7 +788,7 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
             const int64_t b = pb * 2 + h;
             if (b < nblocks) {
                 const float* src = Yp + b * np * 32;
-                for (int e = tid; e < np * 32; e += 256) Ts[(e >> 5) * 65 + h * 32 + (e & 31)] = src[e];
+                for (int e = tid; e < np * 32; e += 256) Ts[(e >> 5) * TS + h * 32 + (e & 31)] = src[e];
             }
         }
         __syncthreads();
@@ -794,8 +799,12 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
             for (int v = 0; v < KV; ++v) acc[u][v] = 0.f;
         for (int c = 0; c < l; ++c) {
             float y[8], sv[KV];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) y[u] = Ts[c * 65 + i0 + 8 * u];  // warp broadcast
+            {
+                const float4 y0 = *reinterpret_cast<const float4*>(Ts + c * TS + 8 * i0);  // warp broadcast
+                const float4 y1 = *reinterpret_cast<const float4*>(Ts + c * TS + 8 * i0 + 4);
+                y[0] = y0.x; y[1] = y0.y; y[2] = y0.z; y[3] = y0.w;
+                y[4] = y1.x; y[5] = y1.y; y[6] = y1.z; y[7] = y1.w;
+            }
 #pragma unroll
             for (int v = 0; v < KV; ++v) sv[v] = Ss[c * KP + KV * j0 + v];
 #pragma unroll
@@ -805,19 +814,18 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int64_t r = pb * 64 + i0 + 8 * u;
+            const int64_t r = pb * 64 + 8 * i0 + u;
             if (r < n) {
 #pragma unroll
                 for (int v = 0; v < KV; ++v)
                     if (KV * j0 + v < k) {
                         if (out != nullptr) out[r * ldo + KV * j0 + v] = acc[u][v];
-                        if (partial != nullptr) {
-                            const double a = fabs((double)acc[u][v]);
-                            if (a > best[v].a || (a == best[v].a && r < best[v].idx)) {
-                                best[v].a = a;
-                                best[v].sgn = signbit(acc[u][v]) ? -1.0 : 1.0;
-                                best[v].idx = r;
-                            }
+                        // rows are visited in increasing order by this thread: a strict > keeps the first maximum
+                        const float a = fabsf(acc[u][v]);
+                        if (a > best_a[v]) {
+                            best_a[v] = a;
+                            best_s[v] = acc[u][v];
+                            best_i[v] = r;
                         }
                     }
             }
@@ -828,7 +836,13 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
         __syncthreads();
         AbsMax* red = reinterpret_cast<AbsMax*>(psm);  // [8][32 * KV]
 #pragma unroll
-        for (int v = 0; v < KV; ++v) red[i0 * (32 * KV) + KV * j0 + v] = best[v];
+        for (int v = 0; v < KV; ++v) {
+            AbsMax b;
+            b.a = (double)best_a[v];
+            b.sgn = signbit(best_s[v]) ? -1.0 : 1.0;
+            b.idx = best_i[v];
+            red[i0 * (32 * KV) + KV * j0 + v] = b;
+        }
         __syncthreads();
         if (i0 == 0) {
 #pragma unroll
@@ -852,7 +866,7 @@ inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, 
                             float* out, int64_t ldo, double* absmax3 = nullptr) {
     if (n == 0 || k == 0) return;
     const int kv = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
-    size_t smem = ((size_t)l * 32 * kv + 65 * (size_t)np) * sizeof(float);
+    size_t smem = ((size_t)l * 32 * kv + 68 * (size_t)np) * sizeof(float);
     static bool attr = false;
     if (!attr) {
         PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
