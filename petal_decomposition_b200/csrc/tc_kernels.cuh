@@ -331,7 +331,8 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 // MMA issue loops are instruction-bound enough that a runtime modulo in them costs 10-20 %.
 //   0  fast     : 4-slot operand ring, one accumulator set, one accumulation chain per group
 //   1  fast2    : tc_xb only, n_pad <= 80: 3-slot ring, two accumulator sets alternating per super-tile, the epilogue of
-//                 tile g drained inside the K loop of tile g+1
+//                 tile g drained inside the K loop of tile g+1.  Not instantiated: measured 6-8 % slower than mode 0 (the
+//                 3-slot ring costs more than the hidden epilogue gains); with a 4-slot ring (n_pad <= 64) it was a wash.
 //   2  precise  : accumulation chains cut (the tensor core adds into its accumulator with truncation):
 //                 tc_xb : 3-slot ring, two sets, chains of 4 K blocks
 //                 tc_atb: 4-slot ring, three one-M-tile buffers, chains of 4 K blocks staggered between the M tiles
