@@ -282,9 +282,14 @@ void launch_xb_tn(petal_ctx* ctx, const XbParams<T>& p, bool aligned) {
     check_launch(ctx);
 }
 
+inline bool launch_xb_dmma(petal_ctx* ctx, const XbParams<double>& p);  // FP64 tensor path, defined with the DMMA kernels
+
 template <typename T>
 void launch_xb(petal_ctx* ctx, const XbParams<T>& p) {
     if (p.n == 0 || p.L == 0) return;
+    if constexpr (sizeof(T) == 8) {
+        if (launch_xb_dmma(ctx, p)) return;
+    }
     constexpr int V = Pack<T>::N;
     bool aligned = (p.K % V == 0) && (p.lda % V == 0) && is_aligned16(p.A) &&
                    (p.mu == nullptr || is_aligned16(p.mu));
@@ -658,6 +663,116 @@ void launch_atb(petal_ctx* ctx, AtbParams<T> p) {
 //   panel_xb   : out[n x k] (row-major) = Y * S,  S[l x k] row-major
 // Skinny, Y-sized passes of the randomized-PCA epilogue (G1 = Y^T Y, scores = Q U_B Sigma).
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// xb on the FP64 tensor path (DMMA): Y[n x L] = (A - mu) * B (+ optional sum of squares of the centred A).
+// CTA = 128 rows x 64 output columns (grid.y walks the column blocks), 8 warps of 16 rows x 64 columns = 2 x 8 DMMA
+// tiles; K in chunks of 16 staged through registers (the next chunk's global loads overlap the current chunk's
+// MMAs).  Row pitches 20 / 68 doubles keep every fragment load of a half-warp on 16 distinct bank pairs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xb_dmma_kernel(XbParams<double> p) {
+    constexpr int BM = 128, BN = 64, KC = 16, LDA = KC + 4, LDB = BN + 4;
+    __shared__ __align__(16) double As[BM * LDA];
+    __shared__ __align__(16) double Bs[KC * LDB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int kq = lane & 3, rq = lane >> 2;
+    const int64_t r0 = (int64_t)blockIdx.x * BM;
+    const int64_t c0 = (int64_t)blockIdx.y * BN;
+    double acc[2][8][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // staging registers: A tile 128 x 16 = 2048 doubles -> 8 per thread (row = tid / 2, 8 consecutive k);
+    // B chunk 16 x 64 = 1024 doubles -> 4 per thread (k = tid / 16, 4 consecutive columns)
+    double a_st[8], b_st[4];
+    const int ar = tid >> 1, ak = (tid & 1) * 8;
+    const int bk = tid >> 4, bc = (tid & 15) * 4;
+    double ss = 0.0;
+    auto load_chunk = [&](int64_t k0) {
+        const int64_t r = r0 + ar;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t k = k0 + ak + j;
+            double v = 0.0;
+            if (r < p.n && k < p.K) v = p.A[r * p.lda + k] - (p.mu ? p.mu[k] : 0.0);
+            a_st[j] = v;
+        }
+        const int64_t k = k0 + bk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t c = c0 + bc + j;
+            double v = 0.0;
+            if (k < p.K && c < p.L) v = p.b_trans ? p.B[c * p.ldb + k] : p.B[k * p.ldb + c];
+            b_st[j] = v;
+        }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            As[ar * LDA + ak + j] = a_st[j];
+            ss += a_st[j] * a_st[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Bs[bk * LDB + bc + j] = b_st[j];
+    };
+    load_chunk(0);
+    store_chunk();
+    __syncthreads();
+    for (int64_t k0 = 0; k0 < p.K; k0 += KC) {
+        const bool has_next = (k0 + KC) < p.K;
+        if (has_next) load_chunk(k0 + KC);
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; ++k4) {
+            double af[2], bf[8];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) af[a] = As[(warp * 16 + a * 8 + rq) * LDA + k4 * 4 + kq];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) bf[b] = Bs[(k4 * 4 + kq) * LDB + b * 8 + rq];
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();
+        if (has_next) {
+            store_chunk();
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int64_t r = r0 + warp * 16 + a * 8 + rq;
+        if (r < p.n) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int64_t c = c0 + b * 8 + 2 * kq;
+                if (c < p.L) p.Y[r * p.ldy + c] = acc[a][b][0];
+                if (c + 1 < p.L) p.Y[r * p.ldy + c + 1] = acc[a][b][1];
+            }
+        }
+    }
+    if (p.sumsq != nullptr && blockIdx.y == 0) {
+        ss = warp_sum(ss);
+        __shared__ double red[8];
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w];
+            atomicAdd(p.sumsq, t);
+        }
+    }
+}
+
+inline bool launch_xb_dmma(petal_ctx* ctx, const XbParams<double>& p) {
+    if (ctx->f64_engine != 1 || p.bias != nullptr || p.n < 256 || p.K < 16 || p.L < 8) return false;
+    dim3 grid((unsigned)ceil_div(p.n, 128), (unsigned)ceil_div(p.L, 64));
+    KTimer kt(ctx, "xb_dmma_f64", (double)p.n * (p.K + p.L) * sizeof(double));
+    xb_dmma_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    check_launch(ctx);
+    return true;
+}
+
 struct AbsMax {
     double a;     // |value|
     double sgn;   // +1 / -1 (f64::signum semantics: -0.0 -> -1)
