@@ -7,16 +7,20 @@
 // core truncates the low 13 mantissa bits itself) and lo = v - hi (exact in fp32), and each product is
 // accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator.
 //
-// Data flow per CTA (persistent, 1 CTA / SM, 384 threads):
-//   warp 8   TMA producer : X tile (+ B / Y tile) -> shared memory ring (mbarrier complete_tx)
-//   warps 0-7 transform   : shared X tile -> registers: subtract mu, split hi/lo -> tcgen05.st into a
-//                           TMEM operand ring (A operand of the MMA lives in TMEM: lane = output row);
-//                           for tc_atb this is also where the X tile is transposed (lane = feature)
-//                           and where the Y tile is transposed + split into K-major Y_hi / Y_lo tiles
-//   warp 9   MMA issuer   : tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory descriptors),
-//                           3 MMAs per K-step, accumulators (2 x 128 x N fp32) stay in TMEM
-//   warps 0-7 epilogue    : tcgen05.ld accumulators -> global (tc_xb: rows of Y; tc_atb: f64 atomics)
-// The centred copy of X never exists; mu is subtracted in the transform stage.
+// Data flow per CTA (persistent, 1 CTA / SM, 640 threads = 20 warps):
+//   warp 16    TMA producer : X tiles -> shared memory ring (mbarrier complete_tx); stages are released as soon as the
+//                             transform warps have read them.  tc_atb with in-kernel B_lo: also feeds the B ring.
+//   warp 19    B side       : tc_xb: TMA producer of the B^T hi / lo tiles.  tc_atb: splitter (Y panel block = B_hi
+//                             operand as loaded; B_lo = y - tf32(y) written next to it).  TMEM alloc / free.
+//   warps 0-15 transform    : shared X tile -> registers: subtract mu, split hi/lo -> tcgen05.st into a TMEM operand
+//                             ring of half-K-block slots (the A operand of the MMA lives in TMEM: lane = output row);
+//                             for tc_atb this is also where the X tile is transposed (lane = feature)
+//   warps 17,18 MMA issuers : one per M tile; tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory descriptors),
+//                             3 MMAs per K-step, accumulators stay in TMEM
+//   warps 0-15 epilogue     : tcgen05.ld accumulators -> Y (tc_xb: panel-major or row-major) / fp32 registers ->
+//                             f64 atomics once per CTA (tc_atb)
+// The centred copy of X never exists; mu is subtracted in the transform stage.  Kernel modes (fast / precise = cut
+// accumulation chains): see ModeTraits.
 #pragma once
 #include <cuda.h>
 
@@ -33,7 +37,7 @@ constexpr int kMT = 2;            // M tiles (128 TMEM lanes each) per CTA
 constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
 constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
 constexpr int kTmemCols = 512;
-constexpr int kYBufs = 3;         // tc_atb: ring of transposed Y tiles (decoupled from the 2 TMEM operand stages)
+constexpr int kYBufs = 3;         // tc_atb, row-major Y: ring of transposed Y tiles (decoupled from the TMEM operand slots)
 constexpr int kASlotsMax = 4;              // TMEM operand ring: one slot per half K block (16 k-values); 3 or 4 slots
 constexpr int kASlotCols = kMT * 32;       // per slot: MT x (16 hi + 16 lo) columns
 // accumulators start after the operand ring: 4 slots -> column 256, one accumulator set (MT x n_pad columns);
@@ -281,11 +285,12 @@ __device__ __forceinline__ uint32_t bar_full_b2(uint32_t base, int s) { return b
 // Work is cut into "groups": one TMEM accumulation each.
 //   tc_xb : group = super-tile of 256 rows, K loop over ceil(K / 32) feature blocks; the epilogue
 //           stores the 256 x n_pad tile of Y.  Groups are dealt round-robin to the persistent CTAs.
-//   tc_atb: the CTA owns one feature group (256 features) and one contiguous slice of rows; a group
-//           is a chunk of <= 1024 rows of that slice (K loop over its 32-row blocks).  The tensor
-//           core adds into its fp32 accumulator with truncation, which biases long chains, so the
-//           chain is cut every chunk: the epilogue adds the chunk result into fp32 registers
-//           (round-to-nearest) and only the CTA's final sums go to global memory (f64 atomics).
+//   tc_atb: the CTA owns one feature group (256 features) and one contiguous slice of rows.  Fast mode: a group
+//           is a chunk of <= 1024 rows of that slice (K loop over its 32-row blocks) = one accumulation chain;
+//           precise mode: one group per CTA, chains of 4 K blocks staggered between the M tiles (ModeTraits).  The
+//           tensor core adds into its fp32 accumulator with truncation, which biases long chains: finished chains
+//           are added into fp32 registers (round-to-nearest) and only the CTA's final sums go to global memory
+//           (f64 atomics).
 // ------------------------------------------------------------------------------------------
 constexpr int kTraceKB = 512;   // K blocks traced (CTA 0 only)
 constexpr int kTraceEvents = 12;
