@@ -204,11 +204,12 @@ def cpu_fit_once(algorithm, x, k, q):
 def cpu_sample_rows(algorithm, d, requested):
     if requested:
         return requested
+    # sized for roughly 10 s of CPU work on 16 host threads (the whole default run must stay within minutes)
     if algorithm == "rpca":
-        return max(1000, int(200_000 * 1024 / d))
+        return max(1000, int(1_000_000 * 1024 / d))
     if algorithm == "pca":
         return max(1000, int(4_000_000 / d))
-    return 200_000
+    return 1_000_000
 
 
 def run_cpu(algorithm, dtype, d, k, q, rows, steps, warmup):
@@ -402,7 +403,7 @@ def main():
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": traffic,
+                    "frac": achieved / hbm_peak, "frac_of_nominal_8000_GBps": achieved / 8000.0, "traffic": traffic,
                     "traffic_source": "ncu dram bytes / algorithmic bytes ratio (profiles/roofline_traffic.json) x this launch's algorithmic bytes",
                     "peak_source": peak_kind,
                     "launches": v["count"], "avg_ms": v["total_ms"] / v["count"],
@@ -416,6 +417,18 @@ def main():
         val, dt = run_cpu(algorithm, dtype, d, k, q, rows, 1, 1)
         cpu = {"value": val, "unit": "samples/s", "cores": blas_threads(), "kind": "port",
                "sample": f"{rows} rows x {d}, one fit ({dt:.1f} s), oracle restatement on numpy/OpenBLAS"}
+        # the crate's own GEMMs (matrixmultiply) are single-threaded: also time the restatement on one BLAS thread,
+        # on a quarter of the sample so the default run stays short
+        try:
+            from threadpoolctl import threadpool_limits
+            rows1 = max(rows // 4, min(rows, 4 * d))
+            with threadpool_limits(limits=1):
+                val1, dt1 = run_cpu(algorithm, dtype, d, k, q, rows1, 1, 0)
+            cpu["value_1_thread"] = val1
+            cpu["sample_1_thread"] = f"{rows1} rows x {d}, one fit ({dt1:.1f} s), 1 BLAS thread"
+        except Exception as e:  # threadpoolctl missing
+            cpu["value_1_thread"] = None
+            cpu["sample_1_thread"] = f"unavailable: {e}"[:120]
 
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
