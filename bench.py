@@ -34,6 +34,7 @@ SEED = 1_234_567_891_011_121_314
 CONFIGS = {
     # name: (algorithm, dtype, n, d, k, q)
     "c2": ("rpca", "f32", 10_000_000, 1024, 64, 4),
+    "c2q7": ("rpca", "f32", 10_000_000, 1024, 64, 7),  # the crate's default number of power iterations
     "c1": ("pca", "f64", 10_000, 100, 10, 0),
     "c3": ("ica", "f32", 1_000_000, 64, 64, 0),
     "c4s": ("pca", "f64", 2_000_000, 512, 64, 0),
@@ -239,7 +240,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = args.rows or n_cfg
     workload = {
-        "c2": "RandomizedPca f32 10Mx1024 k=64 q=4 (configs[1])", "c1": "Pca f64 10000x100 k=10 (configs[0])",
+        "c2": "RandomizedPca f32 10Mx1024 k=64 q=4 (configs[1])",
+        "c2q7": "RandomizedPca f32 10Mx1024 k=64 q=7 (configs[1] with the reference's default power iterations)", "c1": "Pca f64 10000x100 k=10 (configs[0])",
         "c3": "FastIca logcosh f32 1Mx64 (configs[2])", "c4s": "Pca f64 2Mx512 k=64 (configs[3] at d=512)",
         "c5s": "RandomizedPca f32 40Mx256 k=32 q=4 (configs[4] per-GPU shard)"}[args.config]
     config = {"workload": workload, "algorithm": algorithm, "rows_per_gpu": n, "features": d, "n_components": k,
