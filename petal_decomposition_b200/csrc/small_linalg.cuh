@@ -51,7 +51,11 @@ __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, doubl
                                                 double& c, double& s, double* t_out = nullptr) {
     const double na = sqrt(alpha), nb = sqrt(beta);
     if (!(fabs(gamma) > tol * na * nb + noise * (na + nb))) return false;  // also false for NaN/zero rows
-    // (an f32 tangent with f64 normalisation was tried: same step time - the step is not bound by this chain)
+    // (tried in r01, no change in step time: an all-fp32 tangent with a Newton-refined f64 normalisation, and keeping the
+    // two rows in registers between the inner product and the rotation.  ncu on the 64 x 64 case: issue-bound at
+    // ~6200 warp instructions per round-robin step, 0.5 IPC per scheduler - the f64 pipe's quarter-rate issue, not a
+    // particular latency chain or shared-memory bandwidth.  A block-Jacobi / fp32-sweeps + f64-polish engine is the
+    // way forward.)
     const double zeta = (beta - alpha) / (2.0 * gamma);
     const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     c = rsqrt(1.0 + t * t);
