@@ -215,6 +215,9 @@ struct TcParams {
     int b_split;          // tc_atb, panel-major Y: only the Y panel is loaded; a splitter warp derives the y - tf32(y)
                           // operand tile in shared memory (no Y_lo panel in HBM)
     double* sumsq;        // nullable
+    const float* bias;    // tc_xb, row-major Y: per output column, added in the epilogue (nullable)
+    int64_t y_cols;       // tc_xb, row-major Y: columns of a Y row that may be written (the row pitch, or the width of
+                          // a column block when Y is a window of a wider matrix)
     // tc_atb outputs / decomposition
     double* Z;            // [da x ldz] f64, atomically accumulated
     int64_t ldz;
@@ -405,6 +408,40 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
         const int xb_chunks = ATB ? 0 : (panel ? (n_pad - half * 16 + 31) / 32 : n_pad / 16);
         uint32_t pend_gi = 0;
         int pend_next = 0;
+        auto store_rowmajor_chunk = [&](int64_t row0, int c0, const float* w) {
+            // 16x256b pattern: four lanes hold 8 consecutive columns of one row, so every store instruction writes
+            // whole 32 B sectors (8 rows x 32 B).  This warp covers lanes 16*half .. 16*half+15 of its quarter.
+            const int t0 = lane & 3, t1 = lane >> 2;
+            const int64_t ra = row0 + mt * 128 + q * 32 + half * 16 + t1;
+            const int64_t rb = ra + 8;
+            const int ca = c0 + 2 * t0, cb = ca + 8;
+            // optional per-column bias (inverse_transform: + mean)
+            float ba0 = 0.f, ba1 = 0.f, bb0 = 0.f, bb1 = 0.f;
+            if (p.bias != nullptr) {
+                if (ca < p.L) ba0 = p.bias[ca];
+                if (ca + 1 < p.L) ba1 = p.bias[ca + 1];
+                if (cb < p.L) bb0 = p.bias[cb];
+                if (cb + 1 < p.L) bb1 = p.bias[cb + 1];
+            }
+            if (p.y_vec) {
+                if (ra < p.n) {
+                    if (ca + 1 < p.y_cols) *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) = make_float2(w[0] + ba0, w[1] + ba1);
+                    if (cb + 1 < p.y_cols) *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) = make_float2(w[4] + bb0, w[5] + bb1);
+                }
+                if (rb < p.n) {
+                    if (ca + 1 < p.y_cols) *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) = make_float2(w[2] + ba0, w[3] + ba1);
+                    if (cb + 1 < p.y_cols) *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) = make_float2(w[6] + bb0, w[7] + bb1);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int64_t r = (e & 2) ? rb : ra;
+                    const int c = ((e & 4) ? cb : ca) + (e & 1);
+                    const float bv = (e & 4) ? ((e & 1) ? bb1 : bb0) : ((e & 1) ? ba1 : ba0);
+                    if (r < p.n && c < p.y_cols) p.Y[r * p.ldy + c] = w[e] + bv;
+                }
+            }
+        };
         auto xb_drain_chunk = [&](int64_t row0, int buf, int j) {
             const uint32_t acc_col = (uint32_t)(kAccBaseC + buf * kMT * n_pad + mt * n_pad);
             if (panel) {
@@ -434,39 +471,11 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 // four lanes hold 8 consecutive columns of one row, so every store instruction writes
                 // whole 32 B sectors (8 rows x 32 B).
                 const int c0 = 16 * j;
-                const int t0 = lane & 3, t1 = lane >> 2;
                 const uint32_t acc16 = tmem_base + ((uint32_t)(q * 32 + half * 16) << 16) + acc_col;
-                const int64_t ra = row0 + mt * 128 + q * 32 + half * 16 + t1;
-                const int64_t rb = ra + 8;
                 uint32_t w[8];
                 tmem_ld_16x256b_x2(acc16 + (uint32_t)c0, w);
                 tmem_ld_wait();
-                const int ca = c0 + 2 * t0, cb = ca + 8;
-                if (p.y_vec) {
-                    if (ra < p.n) {
-                        if (ca + 1 < p.ldy)
-                            *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) =
-                                make_float2(__uint_as_float(w[0]), __uint_as_float(w[1]));
-                        if (cb + 1 < p.ldy)
-                            *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) =
-                                make_float2(__uint_as_float(w[4]), __uint_as_float(w[5]));
-                    }
-                    if (rb < p.n) {
-                        if (ca + 1 < p.ldy)
-                            *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) =
-                                make_float2(__uint_as_float(w[2]), __uint_as_float(w[3]));
-                        if (cb + 1 < p.ldy)
-                            *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) =
-                                make_float2(__uint_as_float(w[6]), __uint_as_float(w[7]));
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int64_t r = (e & 2) ? rb : ra;
-                        const int c = ((e & 4) ? cb : ca) + (e & 1);
-                        if (r < p.n && c < p.ldy) p.Y[r * p.ldy + c] = __uint_as_float(w[e]);
-                    }
-                }
+                store_rowmajor_chunk(row0, c0, reinterpret_cast<const float*>(w));
             }
         };
         auto xb_drain_step = [&]() {
@@ -550,31 +559,6 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 const float y = valid ? w[jj] : 0.f;
                 yb[(c0 + jj) * 32] = y;
                 if (p.Ylo != nullptr) yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
-            }
-        };
-        auto store_rowmajor_chunk = [&](int64_t row0, int c0, const float* w) {
-            // 16x256b pattern: four lanes hold 8 consecutive columns of one row, so every store instruction writes
-            // whole 32 B sectors (8 rows x 32 B).  This warp covers lanes 16*half .. 16*half+15 of its quarter.
-            const int t0 = lane & 3, t1 = lane >> 2;
-            const int64_t ra = row0 + mt * 128 + q * 32 + half * 16 + t1;
-            const int64_t rb = ra + 8;
-            const int ca = c0 + 2 * t0, cb = ca + 8;
-            if (p.y_vec) {
-                if (ra < p.n) {
-                    if (ca + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + ra * p.ldy + ca) = make_float2(w[0], w[1]);
-                    if (cb + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + ra * p.ldy + cb) = make_float2(w[4], w[5]);
-                }
-                if (rb < p.n) {
-                    if (ca + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + rb * p.ldy + ca) = make_float2(w[2], w[3]);
-                    if (cb + 1 < p.ldy) *reinterpret_cast<float2*>(p.Y + rb * p.ldy + cb) = make_float2(w[6], w[7]);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int64_t r = (e & 2) ? rb : ra;
-                    const int c = ((e & 4) ? cb : ca) + (e & 1);
-                    if (r < p.n && c < p.ldy) p.Y[r * p.ldy + c] = w[e];
-                }
             }
         };
         // tc_xb, registers -> Y for the super-tile starting at row0, registers cleared
@@ -1240,7 +1224,8 @@ inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t sm
 template <typename TS>
 void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_t K, const TS* B, int64_t ldb,
                   bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq,
-                  bool y_panel = false, float* Y_lo_panel = nullptr, int precise = -1) {
+                  bool y_panel = false, float* Y_lo_panel = nullptr, int precise = -1, const float* bias = nullptr,
+                  int64_t y_cols = -1) {
     const int n_pad = round_up(L, 16);
     int stages = 0, stages_b = 0;
     if (!pick_stages(false, n_pad, false, stages, stages_b)) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
@@ -1265,7 +1250,10 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     p.stages_b = stages_b;
     p.Y = Y;
     p.ldy = ldy;
-    p.y_vec = (is_aligned16(Y) && (ldy % 4 == 0)) ? 1 : 0;
+    p.y_cols = (y_cols < 0) ? ldy : y_cols;
+    p.bias = bias;
+    p.L = (int)L;
+    p.y_vec = (is_aligned16(Y) && (ldy % 4 == 0) && (p.y_cols % 2 == 0)) ? 1 : 0;
     p.y_panel = y_panel ? 1 : 0;
     p.Ylo = Y_lo_panel;
     p.sumsq = sumsq;
