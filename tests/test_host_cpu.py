@@ -45,6 +45,25 @@ def test_rng_matches_oracle(lib):
     assert f.dtype == np.float32 and np.array_equal(f, g)
 
 
+def test_rng_golden_fixture(lib):
+    """tests/golden/rng_stream.json pins the restated host RNG stream (oracle and the library's C++ copy)."""
+    import json
+    import struct
+    import petal_decomposition_b200 as pd
+    from oracle.rng import Mcg128Xsl64
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rng_stream.json")))
+    for seed_s, g in fx["seeds"].items():
+        seed = int(seed_s)
+        o = Mcg128Xsl64.from_seed_u128(seed)
+        assert [str(o.next_u64()) for _ in range(16)] == g["next_u64"]
+        want = np.array([struct.unpack(">d", bytes.fromhex(h))[0] for h in g["standard_normal_f64_hex"]])
+        o = Mcg128Xsl64.from_seed_u128(seed)
+        assert np.array_equal(np.array([o.standard_normal() for _ in range(32)]), want)
+        assert str(o.state) == g["state_after_32_normals"]
+        lib_draws = pd.Pcg.from_seed(seed).standard_normal((32,))
+        assert np.array_equal(lib_draws, want)
+
+
 def test_rng_tail_and_moments(lib):
     import petal_decomposition_b200 as pd
     x = pd.Pcg.from_seed(3).standard_normal((400000,))
