@@ -205,7 +205,13 @@ class _Arr:
             if not x.is_contiguous():  # reference: assert!(a.is_standard_layout()) src/linalg.rs:75
                 raise InvalidInput("input must be in the standard (row-major, contiguous) layout")
             self.is_torch = True
-            self.dtype = np.dtype({torch.float32: np.float32, torch.float64: np.float64}.get(x.dtype, None))
+            # explicit lookup: np.dtype(None) would silently be float64 and the library would then read
+            # n*d*8 bytes from a smaller buffer
+            if x.dtype not in (torch.float32, torch.float64):
+                raise InvalidInput("only float32 and float64 are supported")
+            if x.device.type != "cuda":
+                raise InvalidInput("torch inputs must be CUDA tensors (pass numpy arrays for host data)")
+            self.dtype = np.dtype(np.float32 if x.dtype == torch.float32 else np.float64)
             self.ptr = C.c_void_p(x.data_ptr())
             self.shape = tuple(x.shape)
             self.device = x.device
@@ -244,6 +250,25 @@ def _ctx_for(ctx: Context | None) -> Context:
     return ctx if ctx is not None else default_context()
 
 
+def _check_device(ctx: Context, a: "_Arr"):
+    """A device tensor must live on the context's GPU (the library dereferences the pointer there)."""
+    if a.is_torch and a.device.index is not None and a.device.index != ctx.device:
+        raise InvalidInput(f"input is on cuda:{a.device.index} but the context is bound to cuda:{ctx.device}")
+
+
+def _replicate_from_rank0(ctx: Context, m: np.ndarray) -> np.ndarray:
+    """Row-sharded fits keep Omega / w_init replicated: every rank must use rank 0's draw (each rank's own
+    entropy-seeded generator would otherwise give different matrices)."""
+    if ctx.world <= 1:
+        return m
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(m))
+    if dist.get_backend() == "nccl":
+        t = t.cuda(ctx.device)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
 # ---------------------------------------------------------------------------------------------
 # shared transform / inverse_transform (reference src/pca.rs:726-750, 788-811)
 # ---------------------------------------------------------------------------------------------
@@ -252,6 +277,7 @@ def _transform(ctx: Context | None, x, components: np.ndarray, means: np.ndarray
     if a.shape[1] != means.shape[0]:
         raise InvalidInput(f"# of columns should be {means.shape[0]}")
     ctx = _ctx_for(ctx)
+    _check_device(ctx, a)
     comps = np.ascontiguousarray(components, dtype=a.dtype)
     mu = np.ascontiguousarray(means, dtype=a.dtype) if centering else None
     n, d = a.shape
@@ -267,6 +293,7 @@ def _inverse_transform(ctx: Context | None, y, components: np.ndarray, means: np
     if a.shape[1] != components.shape[0]:
         raise InvalidInput(f"# of columns should be {components.shape[0]}")
     ctx = _ctx_for(ctx)
+    _check_device(ctx, a)
     comps = np.ascontiguousarray(components, dtype=a.dtype)
     mu = np.ascontiguousarray(means, dtype=a.dtype) if centering else None
     n, k = a.shape
@@ -339,6 +366,7 @@ class Pca(_PcaBase):
     def _inner_fit(self, x, want_scores: bool):
         a = _Arr(x)
         ctx = _ctx_for(self._ctx)
+        _check_device(ctx, a)
         n, d = a.shape
         k = self._k
         if ctx.world == 1 and n == 0:  # src/pca.rs:207-211 (mean_axis of zero rows is None)
@@ -404,6 +432,7 @@ class RandomizedPca(_PcaBase):
     def _inner_fit(self, x, want_scores: bool, omega: np.ndarray | None = None):
         a = _Arr(x)
         ctx = _ctx_for(self._ctx)
+        _check_device(ctx, a)
         n, d = a.shape
         k = self._k
         if ctx.world == 1 and n == 0:  # src/pca.rs:521-525
@@ -415,7 +444,7 @@ class RandomizedPca(_PcaBase):
         l = k + self.n_oversamples
         if omega is None:  # src/pca.rs:701-705: d x l draws, row-major, f64 -> A
             omega = self.rng.standard_normal((d, l), a.dtype)
-        omega = np.ascontiguousarray(omega, dtype=a.dtype)
+        omega = _replicate_from_rank0(ctx, np.ascontiguousarray(omega, dtype=a.dtype))
         if omega.shape != (d, l):
             raise InvalidInput(f"omega should be {d} x {l}")
         comps = np.empty((k, d), dtype=a.dtype)
@@ -509,6 +538,7 @@ class FastIca:
     def _inner_fit(self, x, want_sources: bool, w_init: np.ndarray | None = None):
         a = _Arr(x)
         ctx = _ctx_for(self._ctx)
+        _check_device(ctx, a)
         n, d = a.shape
         if ctx.world == 1 and n == 0:  # src/ica.rs:174-176
             return a.empty_like_kind((0, min(n, d)))[0] if want_sources else None
@@ -524,7 +554,7 @@ class FastIca:
         nc = min(n_total, d)  # src/ica.rs:173
         if w_init is None:  # src/ica.rs:210-214
             w_init = self.rng.standard_normal((nc, nc), a.dtype)
-        w_init = np.ascontiguousarray(w_init, dtype=a.dtype)
+        w_init = _replicate_from_rank0(ctx, np.ascontiguousarray(w_init, dtype=a.dtype))
         comps = np.empty((nc, d), dtype=a.dtype)
         mean = np.empty(d, dtype=a.dtype)
         n_iter, lim = C.c_int64(0), C.c_double(0.0)

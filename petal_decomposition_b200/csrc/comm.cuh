@@ -68,6 +68,17 @@ inline void allreduce_sum(petal_ctx* ctx, double* buf, size_t count) {
     PETAL_NCCL(nccl_api().AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm->comm, ctx->stream));
 }
 
+// dst <- sum over ranks of src (src is left untouched, so repeating the call with an unchanged src is idempotent);
+// a plain device copy on a single rank.
+inline void allreduce_sum_to(petal_ctx* ctx, const double* src, double* dst, size_t count) {
+    if (count == 0) return;
+    if (ctx->world <= 1) {
+        if (src != dst) PETAL_CUDA(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return;
+    }
+    PETAL_NCCL(nccl_api().AllReduce(src, dst, count, ncclFloat64, ncclSum, ctx->comm->comm, ctx->stream));
+}
+
 // recv[world * count] <- concatenation over ranks of send[count].
 inline void allgather(petal_ctx* ctx, const double* send, double* recv, size_t count) {
     if (ctx->world <= 1) {

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/petal_b200.h"
@@ -58,6 +60,15 @@ struct petal_ctx {
     petal::Comm* comm = nullptr;
     int rank = 0;
     int world = 1;
+    // one call at a time per context (the reference's `&mut self` on fit, src/pca.rs:116): entry points lock this
+    std::mutex mu;
+    // per-context (= per-device) launch state: opted-in dynamic shared memory per kernel, cooperative-launch limits
+    std::vector<std::pair<const void*, size_t>> smem_optin;
+    int coop_ok = -1;
+    int coop_max_ctas = 0;
+    // device-side status word raised by kernels that cannot report through the host (Jacobi sweeps exhausted)
+    int* dev_status = nullptr;
+    bool status_armed = false;  // a kernel that may raise dev_status was launched during this call
 };
 
 namespace petal {
@@ -197,5 +208,24 @@ inline void check_launch(petal_ctx* ctx) {
     ctx->launches++;
     PETAL_CUDA(cudaGetLastError());
 }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remembered per context, never in a
+// process-wide static (several contexts / devices per process are allowed).
+template <typename K>
+inline void ensure_dynamic_smem(petal_ctx* ctx, K kernel, size_t bytes) {
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (auto& e : ctx->smem_optin)
+        if (e.first == key) {
+            if (e.second >= bytes) return;
+            PETAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            e.second = bytes;
+            return;
+        }
+    PETAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->smem_optin.emplace_back(key, bytes);
+}
+
+// status bits of petal_ctx::dev_status
+constexpr int kStatusJacobiNotConverged = 1;
 
 }  // namespace petal

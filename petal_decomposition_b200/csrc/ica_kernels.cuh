@@ -467,7 +467,7 @@ struct IcaFused {
             q.trace = trbuf.p;
         }
         auto launch = [&](auto kernel) {
-            PETAL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemIca));
+            ensure_dynamic_smem(ctx, kernel, kSmemIca);
             KTimer kt(ctx, "ica_fused_f32", (double)p.n * p.d * sizeof(float));
             kernel<<<grid, kThreadsIca, kSmemIca, ctx->stream>>>(q);
             check_launch(ctx);

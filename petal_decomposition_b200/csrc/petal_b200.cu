@@ -22,12 +22,29 @@ const double kGramNoise = 4.0 * 2.220446049250313e-16;
 std::string g_global_error;
 std::mutex g_global_mutex;
 
+// Device-side failures that have no host round trip of their own (Jacobi sweeps exhausted) are collected in
+// ctx->dev_status and turned into the reference's error here (src/linalg.rs:84,115: "did not converge").
+void check_device_status(petal_ctx* ctx) {
+    if (!ctx->status_armed || ctx->dev_status == nullptr) return;
+    ctx->status_armed = false;
+    int h = 0;
+    PETAL_CUDA(cudaMemcpyAsync(&h, ctx->dev_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h != 0) {
+        PETAL_CUDA(cudaMemsetAsync(ctx->dev_status, 0, sizeof(int), ctx->stream));
+        if (h & kStatusJacobiNotConverged) linalg_error("did not converge");
+        linalg_error("device-side failure " + std::to_string(h));
+    }
+}
+
 template <typename F>
 int guarded(petal_ctx* ctx, F&& f) {
     if (!ctx) return PETAL_INVALID_INPUT;
+    std::lock_guard<std::mutex> lock(ctx->mu);  // one call at a time per context
     try {
         PETAL_CUDA(cudaSetDevice(ctx->device));
         f();
+        check_device_status(ctx);
         return PETAL_OK;
     } catch (const Error& e) {
         ctx->last_error = e.msg;
@@ -95,13 +112,15 @@ __global__ void combine_absmax_kernel(const double* __restrict__ gathered, int w
 }
 
 // K[i][j] = Jt[i][j] / sqrt(lambda[i]) * scale   (whitening matrix, reference src/ica.rs:190-203)
+// Directions whose eigenvalue is below cutoff * lambda_max are numerically zero in the Gram matrix (its entries carry
+// eps * lambda_max of noise): they are dropped, not amplified by 1/sqrt(lambda).
 __global__ void whitening_kernel(const double* __restrict__ Jt, const double* __restrict__ lam, int64_t nc,
-                                 int64_t d, double scale, double* __restrict__ K) {
+                                 int64_t d, double scale, double cutoff, double* __restrict__ K) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nc * d) return;
     int64_t i = idx / d;
     double l = lam[i];
-    K[idx] = (l > 0.0) ? Jt[idx] * rsqrt(l) * scale : 0.0;
+    K[idx] = (l > cutoff * lam[0] && l > 0.0) ? Jt[idx] * rsqrt(l) * scale : 0.0;
 }
 
 // Gd[i][j] = HK[i][j] * inv_n - gp[i] * inv_n * W[i][j]     (reference src/ica.rs:334-342)
@@ -145,17 +164,39 @@ __global__ void scale_cols_kernel(double* __restrict__ S, int64_t rows, int64_t 
 // ---------------------------------------------------------------------------------------
 inline void launch1(petal_ctx* ctx) { check_launch(ctx); }
 
-int64_t global_rows(petal_ctx* ctx, int64_t n) {
-    if (ctx->world <= 1) return n;
-    DBuf<double> cnt(ctx, 1);
-    set_value_kernel<<<1, 1, 0, ctx->stream>>>(cnt.p, (double)n);
-    launch1(ctx);
-    allreduce_sum(ctx, cnt.p, 1);
-    double h = 0.0;
-    PETAL_CUDA(cudaMemcpyAsync(&h, cnt.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
-    return (int64_t)(h + 0.5);
+// Total row count over all ranks plus rank-uniform capability bits: every decision that changes which
+// collectives a flow issues (panel layout, one-pass FastICA kernel, tcgen05 engine) must be the same on every
+// rank, so each rank contributes the capabilities it LACKS and a path is taken only when no rank lacks it.
+// One small all-reduce + host read per call (shapes are needed on the host anyway).
+struct GlobalInfo {
+    int64_t n_total;
+    bool cap[4];
+};
+__global__ void set_info_kernel(double* p, double n, int lack0, int lack1, int lack2, int lack3) {
+    p[0] = n;
+    p[1] = lack0;
+    p[2] = lack1;
+    p[3] = lack2;
+    p[4] = lack3;
 }
+GlobalInfo global_info(petal_ctx* ctx, int64_t n, bool c0 = true, bool c1 = true, bool c2 = true, bool c3 = true) {
+    GlobalInfo gi{n, {c0, c1, c2, c3}};
+    if (ctx->world <= 1) return gi;
+    DBuf<double> buf(ctx, 5);
+    set_info_kernel<<<1, 1, 0, ctx->stream>>>(buf.p, (double)n, c0 ? 0 : 1, c1 ? 0 : 1, c2 ? 0 : 1, c3 ? 0 : 1);
+    launch1(ctx);
+    allreduce_sum(ctx, buf.p, 5);
+    double h[5] = {0, 0, 0, 0, 0};
+    PETAL_CUDA(cudaMemcpyAsync(h, buf.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    gi.n_total = (int64_t)(h[0] + 0.5);
+    for (int i = 0; i < 4; ++i) gi.cap[i] = (h[1 + i] == 0.0);
+    return gi;
+}
+int64_t global_rows(petal_ctx* ctx, int64_t n) { return global_info(ctx, n).n_total; }
+
+// would a user buffer be 16 B aligned once it is on the device?  (host inputs are staged into fresh allocations)
+inline bool aligned_on_device(const void* user) { return !is_device_pointer(user) || is_aligned16(user); }
 
 template <typename T>
 struct ColMean {
@@ -417,7 +458,16 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
               int64_t n_over, int64_t n_iter, const T* omega_user, T* comps_u, T* mean_u, T* sing_u, T* tv_u,
               T* scores_u) {
     if (n < 0 || d < 0 || k < 0 || n_over < 0 || n_iter < 0) invalid_input("negative dimension");
-    const int64_t n_total = global_rows(ctx, n);
+    // local capability for the panel-major tcgen05 path (decided for all ranks together, see global_info)
+    bool panel_local = false;
+    if constexpr (sizeof(T) == 4) {
+        const int64_t l_guess = std::min<int64_t>(k + n_over, d);
+        panel_local = ctx->f32_engine == 1 && aligned_on_device(x_user) && tc::xb_supported(nullptr, d, n, d, std::max<int64_t>(l_guess, 1)) &&
+                      n >= 1024 && d >= 32;
+        if (const char* e = getenv("PETAL_PANEL")) panel_local = panel_local && atoi(e) != 0;
+    }
+    const GlobalInfo ginfo = global_info(ctx, n, panel_local);
+    const int64_t n_total = ginfo.n_total;
     if (n_total < k || d < k) invalid_input(dim_message(k));  // src/pca.rs:513-518
     if (n_total == 0 || d == 0) return;                        // src/pca.rs:521-525
     if (omega_user == nullptr) invalid_input("omega (d x (k + n_oversamples) test matrix) is required");
@@ -444,8 +494,10 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     // lines and tc_atb reads its B tiles by TMA without transposing (see tc_kernels.cuh)
     bool panel = false;
     if constexpr (sizeof(T) == 4) {
-        panel = ctx->f32_engine == 1 && tc::xb_supported(X.p, d, n, d, l) && is_aligned16(cm.mu) && n >= 1024 && d >= 32;
-        if (const char* e = getenv("PETAL_PANEL")) panel = panel && atoi(e) != 0;
+        // rank-uniform: every rank can run the panel path on its shard (otherwise ranks would issue different
+        // collectives: the panel path reduces C' = Xc^T Y, the row-major path G1, then [G2 | C'])
+        panel = ginfo.cap[0] && tc::xb_supported(X.p, d, n, d, l) && is_aligned16(cm.mu);
+        if (ginfo.cap[0] && !panel && ctx->world > 1) linalg_error("inconsistent panel-path decision across ranks");
     }
     const int64_t nblk = ceil_div(n, 32);
     DBuf<T> Y(ctx, panel ? (size_t)(nblk * ly * 32) : (size_t)(n * ly));
@@ -777,8 +829,8 @@ ica_update_kernel(const double* __restrict__ Ht /* d x nc */, const double* __re
     // 2 failed: the host redoes this iteration with the Jacobi path), [7] completed fixed-point iterations
     if (out2[6] != 0.0) return;
     extern __shared__ double sm[];
-    const int ld = nc + kIcaLdPad;
-    const int brows = max(nc, d);  // the staging of H^T / K1^T uses d rows
+    const int brows = max(nc, d);  // the staging of H^T / K1^T uses d rows, that of K1 d columns
+    const int ld = brows + kIcaLdPad;
     double* X = sm;
     double* Tm = sm + (size_t)brows * ld;
     double* Y = sm + 2 * (size_t)brows * ld;
@@ -992,16 +1044,26 @@ struct IcaOnePass<float> {
 template <typename T>
 void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, const T* mu, const double* K1,
              int64_t nc, int fun, double tol, int64_t max_iter, int lim_variant, const double* w_init, double* W,
-             int64_t* n_iter_out, double* lim_out) {
+             int64_t* n_iter_out, double* lim_out, bool one_pass_all_ranks = true) {
     if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
     DBuf<double> Wk(ctx, (size_t)(nc * d)), Hg(ctx, (size_t)(nc * d)), Htg(ctx, (size_t)(nc * d + nc)), HK(ctx, (size_t)(nc * nc)),
         Gd(ctx, (size_t)(nc * nc)), W1(ctx, (size_t)(nc * nc)), limd(ctx, 1);
-    const bool one_pass = ica_one_pass_supported<T>(ctx, X, d, n, d, nc);
+    // the one-pass kernel changes how often the host polls (and with it the number of collectives per batch):
+    // taken only when every rank can run it on its shard
+    const bool one_pass = one_pass_all_ranks && ica_one_pass_supported<T>(ctx, X, d, n, d, nc);
+    if (one_pass_all_ranks && !one_pass && ctx->world > 1 && ica_one_pass_supported<T>(ctx, nullptr, d, n, d, nc))
+        linalg_error("inconsistent one-pass decision across ranks");
     DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, one_pass ? (size_t)1 : (size_t)(n * nc));
     double* H = Hg.p;
-    double* Ht = Htg.p;          // [H^T (d x nc) | sum g' (nc)] reduced across ranks together
-    double* gp = Htg.p + nc * d;
     const int htg_n = (int)(nc * d + nc);
+    // Htg = this rank's partial [H^T (d x nc) | sum g' (nc)]; with several ranks the sum over ranks goes to a second
+    // buffer, so that re-issuing the all-reduce with an unconsumed partial (launches of a batch after the device-side
+    // stop flag was raised) cannot scale the sums
+    DBuf<double> Hred(ctx, ctx->world > 1 ? (size_t)htg_n : 0);
+    double* Ht_loc = Htg.p;
+    double* gp_loc = Htg.p + nc * d;
+    double* Ht = ctx->world > 1 ? Hred.p : Htg.p;
+    double* gp = Ht + nc * d;
     const double inv_n = 1.0 / (double)n_total;
     int64_t iters = max_iter;
     double lim = 0.0;
@@ -1009,17 +1071,11 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
     DBuf<double> state(ctx, 8);
     state.zero();
     Htg.zero();
-    const size_t upd_smem = 3 * (size_t)std::max(nc, d) * (nc + kIcaLdPad) * sizeof(double);
-    if (fused) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            PETAL_CUDA(cudaFuncSetAttribute(ica_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            3 * kIcaFusedMax * (kIcaFusedMax + kIcaLdPad) * (int)sizeof(double)));
-            attr_set = true;
-        }
-    }
+    const size_t upd_smem = 3 * (size_t)std::max(nc, d) * (std::max(nc, d) + kIcaLdPad) * sizeof(double);
+    if (fused)
+        ensure_dynamic_smem(ctx, ica_update_kernel<T>, 3 * kIcaFusedMax * (kIcaFusedMax + kIcaLdPad) * sizeof(double));
     IcaOnePass<T> pass;
-    if (one_pass) pass.init(ctx, X, d, n, d, mu, nc, fun, Ht, gp, state.p);
+    if (one_pass) pass.init(ctx, X, d, n, d, mu, nc, fun, Ht_loc, gp_loc, state.p);
     auto make_wt = [&]() {
         // W~ = W K1 so that W x1 = W~ (x - mu): the whitened copy is never materialised
         const double* Wfull = W;
@@ -1064,13 +1120,13 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
             // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
             gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
             // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
-            PETAL_CUDA(cudaMemsetAsync(gp, 0, (size_t)nc * sizeof(double), ctx->stream));
-            launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp);
+            PETAL_CUDA(cudaMemsetAsync(gp_loc, 0, (size_t)nc * sizeof(double), ctx->stream));
+            launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp_loc);
             // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening],
             // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
-            gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht);
+            gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht_loc);
         }
-        allreduce_sum(ctx, Htg.p, (size_t)htg_n);
+        if (ctx->world > 1) allreduce_sum_to(ctx, Htg.p, Hred.p, (size_t)htg_n);
     };
     // small half on the Jacobi path (any nc; also the fallback when Newton-Schulz hits a singular Gd)
     auto slow_update = [&]() {
@@ -1144,7 +1200,9 @@ void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun,
                  int lim_variant, const T* w_init_user, T* comps_u, T* mean_u, int64_t* n_iter_u, double* lim_u,
                  T* sources_u) {
     if (n < 0 || d < 0 || max_iter < 0) invalid_input("negative dimension");
-    const int64_t n_total = global_rows(ctx, n);
+    const bool one_pass_local = aligned_on_device(x_user) && ica_one_pass_supported<T>(ctx, nullptr, d, n, d, std::min<int64_t>(d, 64));
+    const GlobalInfo ginfo = global_info(ctx, n, one_pass_local);
+    const int64_t n_total = ginfo.n_total;
     if (n_total == 0 || d == 0) return;  // src/ica.rs:174-176
     const int64_t nc = std::min<int64_t>(n_total, d);  // src/ica.rs:173
     if (w_init_user == nullptr) invalid_input("w_init (nc x nc) is required");
@@ -1162,17 +1220,19 @@ void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun,
     centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
     jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p, kGramNoise);
     DBuf<double> K(ctx, (size_t)(nc * d)), K1(ctx, (size_t)(nc * d));
-    whitening_kernel<<<(unsigned)ceil_div(nc * d, 256), 256, 0, ctx->stream>>>(Jt.p, lam.p, nc, d, 1.0, K.p);
+    const double wcut = 64.0 * 2.220446049250313e-16;  // relative eigenvalue floor of an f64-accumulated Gram matrix
+    whitening_kernel<<<(unsigned)ceil_div(nc * d, 256), 256, 0, ctx->stream>>>(Jt.p, lam.p, nc, d, 1.0, wcut, K.p);
     launch1(ctx);
     whitening_kernel<<<(unsigned)ceil_div(nc * d, 256), 256, 0, ctx->stream>>>(Jt.p, lam.p, nc, d,
-                                                                              std::sqrt((double)n_total), K1.p);
+                                                                              std::sqrt((double)n_total), wcut, K1.p);
     launch1(ctx);
 
     DBuf<double> Wd(ctx, (size_t)(nc * nc)), Winit_d(ctx, (size_t)(nc * nc));
     launch_cast<T, double>(ctx, Winit.p, Winit_d.p, nc * nc);
     int64_t iters = 0;
     double lim = 0.0;
-    ica_par<T>(ctx, X.p, n, d, n_total, cm.mu, K1.p, nc, fun, tol, max_iter, lim_variant, Winit_d.p, Wd.p, &iters, &lim);
+    ica_par<T>(ctx, X.p, n, d, n_total, cm.mu, K1.p, nc, fun, tol, max_iter, lim_variant, Winit_d.p, Wd.p, &iters, &lim,
+               ginfo.cap[0]);
 
     // components = W K (src/ica.rs:217)
     DBuf<double> Cd(ctx, (size_t)(nc * d));
@@ -1220,6 +1280,8 @@ int petal_ctx_create(int device, petal_ctx** out) {
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
         PETAL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        PETAL_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->dev_status), sizeof(int)));
+        PETAL_CUDA(cudaMemset(ctx->dev_status, 0, sizeof(int)));
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             // keep freed workspaces in the stream-ordered pool: a fit re-uses multi-GB buffers (Y, scores)
@@ -1242,6 +1304,7 @@ void petal_ctx_destroy(petal_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     delete ctx->comm;
+    if (ctx->dev_status) cudaFree(ctx->dev_status);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

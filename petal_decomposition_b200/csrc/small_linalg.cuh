@@ -78,7 +78,8 @@ __device__ __forceinline__ double group16_sum(double v, unsigned mask) {
 __global__ void __launch_bounds__(kJacobiSmemThreads)
 jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restrict__ Aout,
                    double* __restrict__ Jt, double* __restrict__ sig, int max_sweeps, double tol,
-                   double noise_rel, const int* __restrict__ run_flag, int* __restrict__ info) {
+                   double noise_rel, const int* __restrict__ run_flag, int* __restrict__ info,
+                   int* __restrict__ status) {
     if (run_flag != nullptr && *run_flag == 0) return;  // fast path succeeded: nothing to do
     extern __shared__ double sm[];
     double* M = sm;                       // m x len
@@ -107,6 +108,7 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
 
     const int me = (m + 1) & ~1;
     int sweeps = 0;
+    bool converged = (m <= 1);
     // one 16-lane group per row pair: all pairs of a round-robin step run concurrently
     const int gid = tid >> 4, gl = tid & 15, ngroups = kJacobiSmemThreads / 16;
     const unsigned gmask = 0xFFFFu << (lane & 16);
@@ -159,8 +161,14 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
         __syncthreads();
         if (tid == 0) rotated = 0;
         __syncthreads();
-        if (!r) break;
+        if (!r) {
+            converged = true;
+            break;
+        }
     }
+    // sweeps exhausted while rotations were still being applied: the reference's LAPACK drivers return info > 0
+    // here (src/linalg.rs:84,115 -> "did not converge"); the host turns this bit into PETAL_LINALG_ERROR
+    if (!converged && tid == 0 && status != nullptr) atomicOr(status, kStatusJacobiNotConverged);
 
     // norms
     for (int j = warp; j < m; j += nwarps) {
@@ -270,7 +278,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
 __global__ void __launch_bounds__(256)
 jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ J, double* __restrict__ nrm2, int me,
                    int max_sweeps, double tol, double noise_rel, unsigned* __restrict__ bar, int* __restrict__ rot,
-                   int* __restrict__ info) {
+                   int* __restrict__ info, int* __restrict__ status) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ double red[8];
     unsigned target = 0;
@@ -291,6 +299,7 @@ jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
     };
     double noise = 0.0;
     int sweeps = 0;
+    bool converged = (m <= 1);
     for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
         for (int j = blockIdx.x; j < m; j += gridDim.x) {
             const double a = row_norm2(j);
@@ -351,8 +360,12 @@ jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
             grid_barrier(bar, target);
         }
         sweeps = sweep + 1;
-        if (reinterpret_cast<volatile int*>(rot)[sweep] == 0) break;  // written before the last barrier of the sweep: same value in every CTA
+        if (reinterpret_cast<volatile int*>(rot)[sweep] == 0) {  // written before the last barrier of the sweep: same value in every CTA
+            converged = true;
+            break;
+        }
     }
+    if (blockIdx.x == 0 && tid == 0 && !converged && status != nullptr) atomicOr(status, kStatusJacobiNotConverged);
     if (blockIdx.x == 0 && tid == 0 && info) info[0] = sweeps;
 }
 
@@ -431,13 +444,9 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     size_t smem = ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double);
     const bool use_smem = !force_global && smem <= 200 * 1024;
     KTimer kt(ctx, use_smem ? "jacobi_smem" : "jacobi_global", 0.0);
+    ctx->status_armed = true;
     if (use_smem) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            PETAL_CUDA(cudaFuncSetAttribute(jacobi_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            200 * 1024));
-            attr_set = true;
-        }
+        ensure_dynamic_smem(ctx, jacobi_smem_kernel, 200 * 1024);
         DBuf<int> info;
         const bool want_info = getenv("PETAL_JACOBI_INFO") != nullptr;
         if (want_info) {
@@ -445,7 +454,8 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
             info.zero();
         }
         jacobi_smem_kernel<<<1, kJacobiSmemThreads, smem, ctx->stream>>>(A, (int)m, (int)len, Aout, Jt, sig,
-                                                                         max_sweeps, tol, input_noise_rel, run_flag, info.p);
+                                                                         max_sweeps, tol, input_noise_rel, run_flag, info.p,
+                                                                         ctx->dev_status);
         check_launch(ctx);
         if (want_info) {
             int h = 0;
@@ -470,22 +480,19 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     const int me = (int)((m + 1) & ~(int64_t)1);
     int sweeps = 0;
     // persistent cooperative kernel (one launch for all sweeps) when the device supports it
-    static int coop_ok = -1;
-    static int coop_max_ctas = 0;
-    if (coop_ok < 0) {
-        int dev = 0, attr = 0, per_sm = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
+    if (ctx->coop_ok < 0) {
+        int attr = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, ctx->device);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_coop_kernel, 256, 0);
-        coop_max_ctas = per_sm * ctx->sm_count;
-        coop_ok = (attr != 0 && coop_max_ctas > 0 && getenv("PETAL_JACOBI_COOP_OFF") == nullptr) ? 1 : 0;
+        ctx->coop_max_ctas = per_sm * ctx->sm_count;
+        ctx->coop_ok = (attr != 0 && ctx->coop_max_ctas > 0 && getenv("PETAL_JACOBI_COOP_OFF") == nullptr) ? 1 : 0;
     }
-    if (coop_ok == 1 && m > 1) {
+    if (ctx->coop_ok == 1 && m > 1) {
         DBuf<unsigned> bar(ctx, 1);
         DBuf<int> rot(ctx, (size_t)max_sweeps + 1);
         bar.zero();
         rot.zero();
-        int grid = std::min<int>(me / 2, coop_max_ctas);
+        int grid = std::min<int>(me / 2, ctx->coop_max_ctas);
         grid = std::max(grid, 1);
         double* Mp = M.p;
         double* Jp = J.p;
@@ -496,7 +503,8 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
         int* rp = rot.p;
         int* ip = rot.p + max_sweeps;
         int mee = me;
-        void* args[] = {&Mp, &mi, &li, &Jp, &np, &mee, &ms, &tl, &nr, &bp, &rp, &ip};
+        int* sp = ctx->dev_status;
+        void* args[] = {&Mp, &mi, &li, &Jp, &np, &mee, &ms, &tl, &nr, &bp, &rp, &ip, &sp};
         PETAL_CUDA(cudaLaunchCooperativeKernel((void*)jacobi_coop_kernel, dim3((unsigned)grid), dim3(256), args, 0, ctx->stream));
         check_launch(ctx);
         row_norm_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, nrm.p);
@@ -517,6 +525,7 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
         PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
         sweeps = sweep + 1;
         if (!h) break;
+        if (sweep == max_sweeps - 1) linalg_error("did not converge");  // src/linalg.rs:84,115
     }
     row_norm_kernel<<<(unsigned)m, 256, 0, ctx->stream>>>(M.p, (int)m, (int)len, nrm.p);
     check_launch(ctx);
@@ -642,12 +651,8 @@ chol_inverse_kernel(const double* __restrict__ G, int m, double cutoff, double* 
 inline bool chol_supported(int64_t m) { return m >= 1 && m <= kCholMax; }
 
 inline void launch_chol_inverse(petal_ctx* ctx, const double* G, int64_t m, double cutoff, double* P, int* fail) {
-    static bool attr_set = false;
     size_t smem = 2 * (size_t)m * (m + 1) * sizeof(double);
-    if (!attr_set) {
-        PETAL_CUDA(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    ensure_dynamic_smem(ctx, chol_inverse_kernel, 200 * 1024);
     KTimer kt(ctx, "cholesky", 0.0);
     chol_inverse_kernel<<<1, 256, smem, ctx->stream>>>(G, (int)m, cutoff, P, fail);
     check_launch(ctx);

@@ -982,13 +982,9 @@ inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, 
     if (n == 0 || k == 0) return;
     const int kv = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
     size_t smem = ((size_t)l * 32 * kv + 68 * (size_t)np) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        PETAL_CUDA(cudaFuncSetAttribute(panel_xb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr = true;
-    }
+    ensure_dynamic_smem(ctx, panel_xb_kernel<1>, 100 * 1024);
+    ensure_dynamic_smem(ctx, panel_xb_kernel<2>, 100 * 1024);
+    ensure_dynamic_smem(ctx, panel_xb_kernel<4>, 100 * 1024);
     const int64_t nblocks = ceil_div(n, 32);
     const int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->sm_count * 4);
     smem = std::max(smem, (size_t)8 * 32 * kv * sizeof(AbsMax));

@@ -1185,11 +1185,7 @@ inline bool xb_supported(const void* A, int64_t lda, int64_t n, int64_t K, int64
 
 template <bool ATB, int NP, bool PANEL, int MODE>
 inline void launch_kernel(petal_ctx* ctx, const TcParams& p, int grid, size_t smem) {
-    static size_t cur = 0;
-    if (smem > cur) {
-        PETAL_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<ATB, NP, PANEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
-    }
+    ensure_dynamic_smem(ctx, tc_gemm_kernel<ATB, NP, PANEL, MODE>, smem);
     const char* trace_path = getenv("PETAL_TC_TRACE");
     if (trace_path == nullptr) {
         tc_gemm_kernel<ATB, NP, PANEL, MODE><<<grid, kThreads, smem, ctx->stream>>>(p);
