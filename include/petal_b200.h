@@ -163,10 +163,20 @@ int petal_fastica_fit_f64(petal_ctx* ctx, const double* x, int64_t n, int64_t d,
 
 /* ---- building blocks exposed for unit tests (tests/ call these through the same ABI) -----
  * ica_par (src/ica.rs:319-361) on an already-whitened nc x n matrix given as its transpose
- * x1t[n*nc] (samples x components, row-major); w_out[nc*nc]. */
+ * x1t[n*nc] (samples x components, row-major); w_init / w_out[nc*nc] are f64 for both data types (the small
+ * side is f64 on the device).  The f32 entry runs the one-pass tcgen05 kernel when the shape allows. */
+int petal_ica_par_f32(petal_ctx* ctx, const float* x1t, int64_t n, int64_t nc, int fun, double tol,
+                      int64_t max_iter, int lim_variant, const double* w_init, double* w_out,
+                      int64_t* n_iter, double* final_lim);
 int petal_ica_par_f64(petal_ctx* ctx, const double* x1t, int64_t n, int64_t nc, int fun, double tol,
                       int64_t max_iter, int lim_variant, const double* w_init, double* w_out,
                       int64_t* n_iter, double* final_lim);
+/* logcosh (src/ica.rs:383-398) and the exp / cube extensions, elementwise: u[n*nc] (samples x components) is
+ * replaced by g(u), gprime_sum[nc] = sum over the n samples of g'(u) (the reference divides by n).
+ * engine 0: the kernel of the generic path (libm-accurate tanh / exp); engine 1 (f32 only): the device function
+ * the one-pass tcgen05 kernel applies in its epilogue (ex2.approx / rcp.approx tanh). */
+int petal_ica_nonlin_f32(petal_ctx* ctx, float* u, int64_t n, int64_t nc, int fun, int engine, double* gprime_sum);
+int petal_ica_nonlin_f64(petal_ctx* ctx, double* u, int64_t n, int64_t nc, int fun, int engine, double* gprime_sum);
 /* symmetric_decorrelation (src/ica.rs:363-381), textbook (W W^T)^-1/2 W; w[m*m] -> out[m*m]. */
 int petal_symmetric_decorrelation_f64(petal_ctx* ctx, const double* w, int64_t m, double* out);
 /* One-sided Jacobi SVD of a[m*len] (row-major, m <= len or not): a = U diag(s) Vt with

@@ -55,13 +55,30 @@ def logcosh(wx: np.ndarray):
     return g, gp
 
 
+def exp_fun(wx: np.ndarray):
+    """`exp` contrast function. Not in the reference (src/ica.rs:383-398 has logcosh only); BASELINE.json's
+    north_star names it, so it follows the algorithm the crate mirrors: sklearn
+    decomposition/_fastica.py:160-164 (`_exp`): g = x exp(-x^2/2), g' = (1 - x^2) exp(-x^2/2)."""
+    e = np.exp(-(wx * wx) / 2)
+    return wx * e, ((1 - wx * wx) * e).mean(axis=-1)
+
+
+def cube_fun(wx: np.ndarray):
+    """`cube` contrast function, sklearn decomposition/_fastica.py:167-168 (`_cube`): g = x^3, g' = 3 x^2."""
+    return wx ** 3, (3 * wx * wx).mean(axis=-1)
+
+
+G_FUNS = {"logcosh": logcosh, "exp": exp_fun, "cube": cube_fun}
+
+
 def ica_par(x1: np.ndarray, tol: float, max_iter: int, w_init: np.ndarray,
-            symdec: str = "textbook", lim: str = "rowrow"):
+            symdec: str = "textbook", lim: str = "rowrow", fun: str = "logcosh"):
     """reference src/ica.rs:319-361. x1 is nc x n (whitened, features x samples)."""
+    g = G_FUNS[fun]
     w = symmetric_decorrelation(w_init, symdec)  # ica.rs:329
     p_inv = x1.dtype.type(1.0) / x1.dtype.type(x1.shape[1])
     for i in range(max_iter):
-        gwtx, g_wtx = logcosh(w @ x1)  # ica.rs:332
+        gwtx, g_wtx = g(w @ x1)  # ica.rs:332
         gd = gwtx @ x1.T  # ica.rs:333
         gd = gd * p_inv - g_wtx[:, None] * w  # ica.rs:334-342
         w1 = symmetric_decorrelation(gd, symdec)  # ica.rs:343

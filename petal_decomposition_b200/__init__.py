@@ -11,12 +11,12 @@ _cabi.load()  # no CPU fallback: the CUDA library must exist
 
 from .api import (CUBE, EXP, LOGCOSH, Context, DecompositionError, FastIca, FastIcaBuilder,  # noqa: E402,F401
                   InvalidInput, LinalgError, Pca, PcaBuilder, Pcg, RandomizedPca, RandomizedPcaBuilder,
-                  colmean_gram, default_context, ica_par, set_default_context, small_svd,
+                  colmean_gram, default_context, ica_par, logcosh, set_default_context, small_svd,
                   symmetric_decorrelation, xty)
 
 __all__ = [
     "Pca", "PcaBuilder", "RandomizedPca", "RandomizedPcaBuilder", "FastIca", "FastIcaBuilder",
     "DecompositionError", "InvalidInput", "LinalgError", "Pcg", "Context", "default_context",
-    "set_default_context", "ica_par", "symmetric_decorrelation", "small_svd", "colmean_gram", "xty",
+    "set_default_context", "ica_par", "logcosh", "symmetric_decorrelation", "small_svd", "colmean_gram", "xty",
     "LOGCOSH", "EXP", "CUBE",
 ]

@@ -24,6 +24,7 @@ _TYPED = {
                                   C.POINTER(c_i64), C.POINTER(c_dbl), c_vp]),
     "petal_colmean_gram": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "petal_xty": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "petal_ica_nonlin": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp]),
 }
 SYMBOLS = {
     "petal_ctx_create": (c_int, [c_int, C.POINTER(c_vp)]),
@@ -47,6 +48,8 @@ SYMBOLS = {
     "petal_rng_get_state": (None, [c_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "petal_rng_normal_f64": (None, [c_vp, c_vp, c_i64]),
     "petal_rng_normal_f32": (None, [c_vp, c_vp, c_i64]),
+    "petal_ica_par_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_int, c_vp, c_vp,
+                                  C.POINTER(c_i64), C.POINTER(c_dbl)]),
     "petal_ica_par_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_int, c_vp, c_vp,
                                   C.POINTER(c_i64), C.POINTER(c_dbl)]),
     "petal_symmetric_decorrelation_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -612,17 +612,34 @@ class FastIcaBuilder:
 # ---------------------------------------------------------------------------------------------
 def ica_par(x1t: np.ndarray, tol: float, max_iter: int, w_init: np.ndarray, fun: int = LOGCOSH,
             lim_variant: int = 0, ctx: Context | None = None):
-    """reference `ica_par` (src/ica.rs:319-361); x1t is the whitened data as samples x components."""
+    """reference `ica_par` (src/ica.rs:319-361); x1t is the whitened data as samples x components
+    (float64, or float32 to run the f32 engines); W is f64 either way."""
     ctx = _ctx_for(ctx)
-    x1t = np.ascontiguousarray(x1t, dtype=np.float64)
+    x1t = np.asarray(x1t)
+    x1t = np.ascontiguousarray(x1t, dtype=np.float32 if x1t.dtype == np.float32 else np.float64)
     w_init = np.ascontiguousarray(w_init, dtype=np.float64)
     n, nc = x1t.shape
     w = np.empty((nc, nc))
     n_iter, lim = C.c_int64(0), C.c_double(0.0)
-    ctx.check(ctx.lib.petal_ica_par_f64(ctx.handle, _np_ptr(x1t), n, nc, fun, float(tol), int(max_iter),
-                                        int(lim_variant), _np_ptr(w_init), _np_ptr(w), C.byref(n_iter),
-                                        C.byref(lim)))
+    fn = getattr(ctx.lib, f"petal_ica_par_{_SUFFIX[x1t.dtype]}")
+    ctx.check(fn(ctx.handle, _np_ptr(x1t), n, nc, fun, float(tol), int(max_iter), int(lim_variant), _np_ptr(w_init),
+                 _np_ptr(w), C.byref(n_iter), C.byref(lim)))
     return w, int(n_iter.value)
+
+
+def logcosh(wx: np.ndarray, fun: int = LOGCOSH, engine: int = 0, ctx: Context | None = None):
+    """reference `logcosh` (src/ica.rs:383-398): wx is components x samples; returns (g(wx), row means of g'(wx)).
+    engine 1 applies the device function of the one-pass tcgen05 kernel's epilogue (f32 only)."""
+    ctx = _ctx_for(ctx)
+    wx = np.asarray(wx)
+    if wx.dtype not in _SUFFIX:
+        raise InvalidInput("only float32 and float64 are supported")
+    nc, n = wx.shape
+    u = np.ascontiguousarray(wx.T)  # samples x components, the layout of the streaming pass
+    gsum = np.zeros(nc)
+    fn = getattr(ctx.lib, f"petal_ica_nonlin_{_SUFFIX[wx.dtype]}")
+    ctx.check(fn(ctx.handle, _np_ptr(u), n, nc, int(fun), int(engine), _np_ptr(gsum)))
+    return np.ascontiguousarray(u.T), (gsum / n).astype(wx.dtype)
 
 
 def symmetric_decorrelation(w: np.ndarray, ctx: Context | None = None) -> np.ndarray:

@@ -106,6 +106,18 @@ __device__ __forceinline__ float ica_g_acc(float u, float& acc) {
     }
 }
 
+// test hook: the epilogue's device function applied elementwise to U[n x nc] (see petal_ica_nonlin_f32)
+template <int FUN>
+__global__ void ica_g_probe_kernel(float* __restrict__ U, int64_t n, int64_t nc, double* __restrict__ gsum) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * nc) return;
+    float acc = 0.f;
+    const float g = ica_g_acc<FUN>(U[i], acc);
+    U[i] = g;
+    // the kernel carries sum g^2 for logcosh and turns it into sum (1 - g^2) at the end
+    atomicAdd(&gsum[i % nc], (double)(FUN == PETAL_ICA_LOGCOSH ? 1.0f - acc : acc));
+}
+
 constexpr int kTraceTiles = 64;
 constexpr int kTraceEv = 16;
 __device__ __forceinline__ void ica_trace(const IcaParams& p, int ev, uint32_t it) {

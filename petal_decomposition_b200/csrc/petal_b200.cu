@@ -1253,6 +1253,34 @@ void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun,
     finish_call(ctx, comps.to_host || mean.to_host || sources.to_host);
 }
 
+template <typename T>
+void ica_nonlin(petal_ctx* ctx, T* u_user, int64_t n, int64_t nc, int fun, int engine, double* gsum_user) {
+    if (n <= 0 || nc <= 0) invalid_input("empty input");
+    if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
+    DevIn<T> Uin(ctx, u_user, (size_t)(n * nc));
+    DevOut<T> U(ctx, u_user, (size_t)(n * nc));
+    DevOut<double> gs(ctx, gsum_user, (size_t)nc);
+    if (!U || !gs) invalid_input("output buffer is null");
+    if (U.p != Uin.p) PETAL_CUDA(cudaMemcpyAsync(U.p, Uin.p, (size_t)(n * nc) * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    PETAL_CUDA(cudaMemsetAsync(gs.p, 0, (size_t)nc * sizeof(double), ctx->stream));
+    if (engine == 0) {
+        launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gs.p);
+    } else {
+        if constexpr (sizeof(T) == 4) {
+            const unsigned blocks = (unsigned)ceil_div(n * nc, 256);
+            if (fun == PETAL_ICA_LOGCOSH) ica::ica_g_probe_kernel<PETAL_ICA_LOGCOSH><<<blocks, 256, 0, ctx->stream>>>(U.p, n, nc, gs.p);
+            else if (fun == PETAL_ICA_EXP) ica::ica_g_probe_kernel<PETAL_ICA_EXP><<<blocks, 256, 0, ctx->stream>>>(U.p, n, nc, gs.p);
+            else ica::ica_g_probe_kernel<PETAL_ICA_CUBE><<<blocks, 256, 0, ctx->stream>>>(U.p, n, nc, gs.p);
+            launch1(ctx);
+        } else {
+            invalid_input("engine 1 (one-pass kernel epilogue) is f32 only");
+        }
+    }
+    U.commit(ctx);
+    gs.commit(ctx);
+    finish_call(ctx, U.to_host || gs.to_host);
+}
+
 }  // namespace
 
 // =========================================================================================
@@ -1490,24 +1518,36 @@ PETAL_DEFINE_XTY(f64, double)
 PETAL_DEFINE_TYPED(f32, float)
 PETAL_DEFINE_TYPED(f64, double)
 
-int petal_ica_par_f64(petal_ctx* ctx, const double* x1t, int64_t n, int64_t nc, int fun, double tol,
-                      int64_t max_iter, int lim_variant, const double* w_init, double* w_out, int64_t* n_iter,
-                      double* final_lim) {
-    return guarded(ctx, [&] {
-        if (n <= 0 || nc <= 0) invalid_input("empty input");
-        const int64_t n_total = global_rows(ctx, n);
-        DevIn<double> X(ctx, x1t, (size_t)(n * nc)), Wi(ctx, w_init, (size_t)(nc * nc));
-        DevOut<double> W(ctx, w_out, (size_t)(nc * nc));
-        if (!W) invalid_input("output buffer is null");
-        int64_t iters = 0;
-        double lim = 0.0;
-        ica_par<double>(ctx, X.p, n, nc, n_total, nullptr, nullptr, nc, fun, tol, max_iter, lim_variant, Wi.p, W.p,
-                        &iters, &lim);
-        if (n_iter) *n_iter = iters;
-        if (final_lim) *final_lim = lim;
-        W.commit(ctx);
-        finish_call(ctx, W.to_host);
-    });
+#define PETAL_DEFINE_ICA_PAR(SUFFIX, T)                                                                        \
+    int petal_ica_par_##SUFFIX(petal_ctx* ctx, const T* x1t, int64_t n, int64_t nc, int fun, double tol,           \
+                               int64_t max_iter, int lim_variant, const double* w_init, double* w_out,            \
+                               int64_t* n_iter, double* final_lim) {                                              \
+        return guarded(ctx, [&] {                                                                                 \
+            if (n <= 0 || nc <= 0) invalid_input("empty input");                                                  \
+            const bool one_pass_local = aligned_on_device(x1t) && ica_one_pass_supported<T>(ctx, nullptr, nc, n, nc, nc); \
+            const GlobalInfo gi = global_info(ctx, n, one_pass_local);                                            \
+            DevIn<T> X(ctx, x1t, (size_t)(n * nc));                                                               \
+            DevIn<double> Wi(ctx, w_init, (size_t)(nc * nc));                                                     \
+            DevOut<double> W(ctx, w_out, (size_t)(nc * nc));                                                      \
+            if (!W) invalid_input("output buffer is null");                                                       \
+            int64_t iters = 0;                                                                                    \
+            double lim = 0.0;                                                                                     \
+            ica_par<T>(ctx, X.p, n, nc, gi.n_total, nullptr, nullptr, nc, fun, tol, max_iter, lim_variant, Wi.p,  \
+                       W.p, &iters, &lim, gi.cap[0]);                                                             \
+            if (n_iter) *n_iter = iters;                                                                          \
+            if (final_lim) *final_lim = lim;                                                                      \
+            W.commit(ctx);                                                                                        \
+            finish_call(ctx, W.to_host);                                                                          \
+        });                                                                                                       \
+    }
+PETAL_DEFINE_ICA_PAR(f32, float)
+PETAL_DEFINE_ICA_PAR(f64, double)
+
+int petal_ica_nonlin_f32(petal_ctx* ctx, float* u, int64_t n, int64_t nc, int fun, int engine, double* gprime_sum) {
+    return guarded(ctx, [&] { ica_nonlin<float>(ctx, u, n, nc, fun, engine, gprime_sum); });
+}
+int petal_ica_nonlin_f64(petal_ctx* ctx, double* u, int64_t n, int64_t nc, int fun, int engine, double* gprime_sum) {
+    return guarded(ctx, [&] { ica_nonlin<double>(ctx, u, n, nc, fun, engine, gprime_sum); });
 }
 
 int petal_symmetric_decorrelation_f64(petal_ctx* ctx, const double* w, int64_t m, double* out) {

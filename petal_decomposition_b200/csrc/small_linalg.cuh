@@ -436,7 +436,8 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
                        const int* run_flag = nullptr) {
     if (m == 0) return 0;
     if (m > (int64_t)1 << 20 || len > (int64_t)1 << 30) invalid_input("matrix too large for the Jacobi solver");
-    const int max_sweeps = 60;
+    int max_sweeps = 60;
+    if (const char* e = getenv("PETAL_JACOBI_MAX_SWEEPS")) max_sweeps = std::max(1, atoi(e));  // testing: forces "did not converge"
     // |<a_p, a_q>| <= tol * |a_p| |a_q| counts as orthogonal. The computed inner product carries
     // ~sqrt(len) * eps of rounding noise, so the threshold sits a small factor above that - a
     // tighter one never reports a rotation-free sweep and runs to max_sweeps.
@@ -489,7 +490,7 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     }
     if (ctx->coop_ok == 1 && m > 1) {
         DBuf<unsigned> bar(ctx, 1);
-        DBuf<int> rot(ctx, (size_t)max_sweeps + 1);
+        DBuf<int> rot(ctx, (size_t)max_sweeps + 1);  // [sweep flags | sweeps used]
         bar.zero();
         rot.zero();
         int grid = std::min<int>(me / 2, ctx->coop_max_ctas);

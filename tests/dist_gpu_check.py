@@ -67,6 +67,48 @@ def main():
     _, defect = oica.match_rows(ica.components, oref.components)
     report("fastica f64 unmixing rows", defect < 1e-6, f"defect {defect:.2e} n_iter {ica.n_iter}/{oref.n_iter}")
 
+    # randomized PCA f32: fit_transform scores of the local shard (signs decided across ranks, src/pca.rs:815-850)
+    rp2 = pd.RandomizedPcaBuilder.new(16).seed(seed).n_power_iter(4).build()
+    r0, r1 = shard_rows(x32.shape[0], rank, world)
+    y32 = rp2.fit_transform(np.ascontiguousarray(x32[r0:r1]))
+    yr32 = rref.fit_transform(x32.astype(np.float64), omega.astype(np.float64))[r0:r1]
+    sc = np.abs(yr32).max()
+    report("rpca f32 scores (signs incl.)", np.allclose(y32[:, :8], yr32[:, :8], atol=2e-3 * sc),
+           f"max abs diff {np.max(np.abs(y32[:, :8] - yr32[:, :8])) / sc:.2e} of max |score|")
+
+    # FastICA f32, d = nc = 64: one-pass tcgen05 kernel per rank + 16.6 KB all-reduce per iteration
+    x64c, a64 = synth.mixed_sources(120000, 64, seed=1, dtype=np.float32)
+    r0, r1 = shard_rows(x64c.shape[0], rank, world)
+    ica32 = pd.FastIca.with_seed(seed)
+    s32 = ica32.fit_transform(np.ascontiguousarray(x64c[r0:r1]))
+    oref32 = oica.FastIca()
+    oref32.fit(x64c.astype(np.float64), Mcg128Xsl64.from_seed_u128(seed).normal_matrix(64, 64, np.float32).astype(np.float64))
+    _, defect = oica.match_rows(ica32.components, oref32.components)
+    am = oica.amari_index(ica32.components, a64)
+    report("fastica f32 d=64 unmixing rows", defect < 1e-4 and am < 0.05 and ica32.n_iter < 200,
+           f"defect {defect:.2e} amari {am:.3f} n_iter {ica32.n_iter}/{oref32.n_iter}")
+    report("fastica f32 sources shape", s32.shape == (r1 - r0, 64) and np.isfinite(np.asarray(s32)).all())
+
+    # uneven shards straddling the kernels' row thresholds (1024 rows): every rank must take the same path,
+    # otherwise ranks issue different collectives and hang
+    nt = 1024 * world - 1
+    xs = synth.lowrank_noise(nt, 64, rank=12, decay=0.7, noise=0.01, seed=21, dtype=np.float32)
+    r0, r1 = shard_rows(nt, rank, world)
+    om = Mcg128Xsl64.from_seed_u128(seed).normal_matrix(64, 18, np.float32)
+    rs = pd.RandomizedPcaBuilder.new(8).seed(seed).n_power_iter(3).build()
+    rs.fit(np.ascontiguousarray(xs[r0:r1]))
+    rr = opca.RandomizedPca(8, n_iter=3)
+    rr.fit(xs.astype(np.float64), om.astype(np.float64))
+    err = np.max(np.abs(rs.singular_values() - rr.singular_values()) / rr.singular_values())
+    report("rpca f32 uneven shards around 1024 rows", err < 1e-4, f"rel err {err:.2e}")
+    xi2, _ = synth.mixed_sources(nt, 8, seed=8, dtype=np.float32)
+    ic2 = pd.FastIca.with_seed(seed)
+    ic2.fit(np.ascontiguousarray(xi2[r0:r1]))
+    or2 = oica.FastIca()
+    or2.fit(xi2.astype(np.float64), Mcg128Xsl64.from_seed_u128(seed).normal_matrix(8, 8, np.float32).astype(np.float64))
+    _, defect = oica.match_rows(ic2.components, or2.components)
+    report("fastica f32 uneven shards around 1024 rows", defect < 1e-3, f"defect {defect:.2e} n_iter {ic2.n_iter}/{or2.n_iter}")
+
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{ctx.device}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
