@@ -506,7 +506,8 @@ def main():
             if top in ("atb_dmma_f64", "gemm_dmma_f64", "syrk_dmma_f64"):
                 # FP64 tensor pipe: the Gram passes of exact PCA at d >= ~256 are compute-bound (AI ~ d/8 flop/B);
                 # flops syrk-counted as SURVEY 8(d): d (d + 1) per sample and pass
-                flops = float(n) * d * (d + 1) * v["count"]
+                # rows are summed over the launches through `work` (= rows x d x 8 bytes for a symmetric Gram launch)
+                flops = (v["work"] / (d * 8.0)) * d * (d + 1)
                 achieved = flops / (v["total_ms"] * 1e-3) / 1e12
                 fp64_peak, fp64_src = 40.0, "nominal 40 TFLOP/s (B200 FP64 tensor)"
                 try:

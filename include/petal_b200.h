@@ -198,6 +198,12 @@ int petal_xty_f32(petal_ctx* ctx, const float* x, int64_t n, int64_t d, const fl
 int petal_xty_f64(petal_ctx* ctx, const double* x, int64_t n, int64_t d, const double* mean, const double* y,
                   int64_t l, double* out);
 
+/* ---- measurement utility ------------------------------------------------------------------
+ * FP64 tensor-pipe probe: back-to-back mma.sync.m8n8k4.f64 from registers on every SM (no memory traffic), timed
+ * with CUDA events.  out[0] = TFLOP/s with `ctas_per_sm` CTAs of 8 warps per SM; the denominator of the
+ * "fraction of FP64 tensor peak" figures bench.py reports for exact PCA (profiles/r02_fp64_dmma_peak.json). */
+int petal_probe_dmma_tflops(petal_ctx* ctx, int ctas_per_sm, double* out);
+
 #ifdef __cplusplus
 }
 #endif

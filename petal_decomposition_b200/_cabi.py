@@ -53,6 +53,7 @@ SYMBOLS = {
     "petal_ica_par_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_int, c_vp, c_vp,
                                   C.POINTER(c_i64), C.POINTER(c_dbl)]),
     "petal_symmetric_decorrelation_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "petal_probe_dmma_tflops": (c_int, [c_vp, c_int, c_vp]),
     "petal_small_svd_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
 }
 for _name, _sig in _TYPED.items():

@@ -106,6 +106,12 @@ class Context:
         self.check(self.lib.petal_comm_init(self.handle, buf, int(rank), int(world)))
         self.rank, self.world = int(rank), int(world)
 
+    def probe_dmma_tflops(self, ctas_per_sm: int = 2) -> float:
+        """FP64 tensor-pipe issue-rate probe (register-only DMMA loop), TFLOP/s."""
+        out = C.c_double(0.0)
+        self.check(self.lib.petal_probe_dmma_tflops(self.handle, int(ctas_per_sm), C.byref(out)))
+        return float(out.value)
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.petal_ctx_destroy(self.handle)
@@ -635,7 +641,7 @@ def logcosh(wx: np.ndarray, fun: int = LOGCOSH, engine: int = 0, ctx: Context | 
     if wx.dtype not in _SUFFIX:
         raise InvalidInput("only float32 and float64 are supported")
     nc, n = wx.shape
-    u = np.ascontiguousarray(wx.T)  # samples x components, the layout of the streaming pass
+    u = np.array(wx.T, order="C", copy=True)  # samples x components (the streaming pass's layout); replaced by g(u)
     gsum = np.zeros(nc)
     fn = getattr(ctx.lib, f"petal_ica_nonlin_{_SUFFIX[wx.dtype]}")
     ctx.check(fn(ctx.handle, _np_ptr(u), n, nc, int(fun), int(engine), _np_ptr(gsum)))

@@ -1,0 +1,637 @@
+// Dense f64 work on the d x d side of exact PCA at large d (BASELINE config c4: d = 4096), all on the FP64 tensor
+// path (mma.sync.m8n8k4.f64):
+//
+//   gemm_nn        C = alpha (A - mu) B (+ C)          Q1 = Xc R1^-1 (pass 2 of CholeskyQR2), R = R2 R1, the blocked
+//                                                      Cholesky / triangular-inverse updates
+//   chol_blocked   G = R^T R, P = R^-1                 replaces the single-CTA Cholesky for m > 104
+//   block_jacobi   one-sided block Jacobi SVD of the rows of a matrix: pairs of 32-row blocks, per pair
+//                  G_p = A_p A_p^T (DMMA), a 64 x 64 one-sided Jacobi in shared memory, A_p <- J_p A_p (DMMA)
+//                  replaces the scalar cooperative engine for m >= 2048 (its rotations are DFMA-issue bound:
+//                  ~0.6 s per sweep at m = 4096)
+//
+// Reference: the LAPACK calls these stand in for are gesvd on the centred data (src/pca.rs:216-220 ->
+// src/linalg/lapack.rs:103-132); north_star (1) names the replacement: tall-skinny CholeskyQR2 of Xc, then a
+// one-sided Jacobi SVD of the small R.
+#pragma once
+#include "small_linalg.cuh"
+#include "stream_kernels.cuh"
+
+namespace petal {
+
+// relative entry noise of a Gram matrix accumulated in f64 (orthogonality floor of the inner Jacobi solves)
+constexpr double kGramNoiseRel = 4.0 * 2.220446049250313e-16;
+
+// ------------------------------------------------------------------------------------------
+// gemm_nn: 128 x 128 output tile per CTA, K in chunks of 16 staged through registers (next chunk's global loads
+// overlap the current chunk's MMAs); 8 warps as 4 (rows) x 2 (columns), each 32 x 64 = 4 x 8 DMMA tiles.
+// Tiles are rasterised column-fastest, so the CTAs resident at the same time share their A rows in L2.
+// ------------------------------------------------------------------------------------------
+struct GemmParams {
+    const double* A;   // M x K row-major
+    int64_t lda;
+    const double* B;   // K x N row-major
+    int64_t ldb;
+    double* C;         // M x N row-major
+    int64_t ldc;
+    int64_t M, N, K;
+    const double* mu;  // nullable [K]: A - mu
+    double alpha;
+    int accumulate;    // C += alpha A B instead of C = alpha A B
+    int b_upper;       // B upper triangular (square): rows k > last column of the tile contribute nothing
+    int a_upper;       // A upper triangular (square): columns k < first row of the tile contribute nothing
+    int c_upper;       // only tiles that touch the upper triangle are computed (others left untouched)
+    int tiles_n;
+};
+
+__global__ void __launch_bounds__(256) gemm_nn_dmma_kernel(GemmParams p) {
+    constexpr int BM = 128, BN = 128, KC = 16, LDA = KC + 4, LDB = BN + 4;
+    __shared__ __align__(16) double As[BM * LDA];
+    __shared__ __align__(16) double Bs[KC * LDB];
+    const int tile_m = blockIdx.x / p.tiles_n, tile_n = blockIdx.x % p.tiles_n;
+    if (p.c_upper && tile_n < tile_m) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wi = warp >> 1, wj = warp & 1, kq = lane & 3, rq = lane >> 2;
+    const int64_t r0 = (int64_t)tile_m * BM, c0 = (int64_t)tile_n * BN;
+    int64_t k_begin = p.a_upper ? (r0 / KC) * KC : 0;
+    int64_t k_end = p.b_upper ? min(p.K, c0 + BN) : p.K;
+    double acc[4][8][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // staging: A tile 128 x 16 -> 8 per thread (row = tid / 2, 8 consecutive k); B tile 16 x 128 -> 8 per thread
+    // (k = tid / 16, 8 consecutive columns)
+    double a_st[8], b_st[8];
+    const int ar = tid >> 1, ak = (tid & 1) * 8;
+    const int bk = tid >> 4, bc = (tid & 15) * 8;
+    auto load_chunk = [&](int64_t k0) {
+        const int64_t r = r0 + ar;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t k = k0 + ak + j;
+            double v = 0.0;
+            if (r < p.M && k < k_end) v = p.A[r * p.lda + k] - (p.mu ? p.mu[k] : 0.0);
+            a_st[j] = v;
+        }
+        const int64_t k = k0 + bk;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t c = c0 + bc + j;
+            double v = 0.0;
+            if (k < k_end && c < p.N) v = p.B[k * p.ldb + c];
+            b_st[j] = v;
+        }
+    };
+    auto store_chunk = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) As[ar * LDA + ak + j] = a_st[j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Bs[bk * LDB + bc + j] = b_st[j];
+    };
+    if (k_begin < k_end) {
+        load_chunk(k_begin);
+        store_chunk();
+    }
+    __syncthreads();
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += KC) {
+        const bool has_next = (k0 + KC) < k_end;
+        if (has_next) load_chunk(k0 + KC);
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; ++k4) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[(wi * 32 + a * 8 + rq) * LDA + k4 * 4 + kq];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) bf[b] = Bs[(k4 * 4 + kq) * LDB + wj * 64 + b * 8 + rq];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();
+        if (has_next) {
+            store_chunk();
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int64_t r = r0 + wi * 32 + a * 8 + rq;
+        if (r >= p.M) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int64_t c = c0 + wj * 64 + b * 8 + 2 * kq;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (c + e < p.N) {
+                    double* dst = p.C + r * p.ldc + c + e;
+                    const double v = p.alpha * acc[a][b][e];
+                    *dst = p.accumulate ? (*dst + v) : v;
+                }
+            }
+        }
+    }
+}
+
+inline void launch_gemm_nn(petal_ctx* ctx, GemmParams p, const char* label = "gemm_dmma_f64") {
+    if (p.M == 0 || p.N == 0) return;
+    const int64_t tiles_m = ceil_div(p.M, 128), tiles_n = ceil_div(p.N, 128);
+    p.tiles_n = (int)tiles_n;
+    KTimer kt(ctx, label, (double)p.M * (p.K + p.N) * sizeof(double));
+    gemm_nn_dmma_kernel<<<(unsigned)(tiles_m * tiles_n), 256, 0, ctx->stream>>>(p);
+    check_launch(ctx);
+}
+
+// convenience: C[M x N] = alpha A[M x K] B[K x N]
+inline void gemm_nn(petal_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                    int64_t M, int64_t N, int64_t K, double alpha = 1.0, bool accumulate = false, bool a_upper = false,
+                    bool b_upper = false, bool c_upper = false, const double* mu = nullptr) {
+    GemmParams p{};
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.mu = mu;
+    p.alpha = alpha; p.accumulate = accumulate ? 1 : 0; p.a_upper = a_upper ? 1 : 0; p.b_upper = b_upper ? 1 : 0;
+    p.c_upper = c_upper ? 1 : 0;
+    launch_gemm_nn(ctx, p);
+}
+
+// ------------------------------------------------------------------------------------------
+// Blocked Cholesky G = R^T R (R upper triangular) and P = R^-1, panels of kCholNB columns.
+//   per panel: diagonal block factorised + inverted in one CTA (shared memory); row panel by one small GEMM with the
+//   inverted diagonal block; trailing update G22 -= R12^T R12 on the DMMA Gram kernel (scale = -1).
+// On exit G holds R in its upper triangle (strictly lower part zeroed), P = R^-1 (upper triangular).
+// *fail is raised (device flag) when a pivot drops below cutoff * max diag: the caller falls back to the
+// eigen-decomposition route, which handles rank-deficient matrices.
+// ------------------------------------------------------------------------------------------
+constexpr int kCholNB = 64;
+constexpr size_t kCholDiagSmem = 2 * (size_t)kCholNB * (kCholNB + 1) * sizeof(double);
+
+// One CTA: factorises the nb x nb diagonal block at G[j0, j0] in place (upper triangle = R_jj), writes R_jj^-1 into
+// Dinv [nb x nb]; maxdiag (device scalar) carries max diag of the ORIGINAL matrix for the pivot test.
+__global__ void __launch_bounds__(256)
+chol_diag_kernel(double* __restrict__ G, int64_t ld, int64_t j0, int nb, double cutoff, const double* __restrict__ maxdiag,
+                 double* __restrict__ Dinv, int* __restrict__ fail) {
+    if (*fail) return;
+    extern __shared__ double csm[];
+    double* A = csm;
+    double* X = csm + kCholNB * (kCholNB + 1);
+    __shared__ int bad;
+    const int ldl = kCholNB + 1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < nb * nb; i += 256) {
+        A[(i / nb) * ldl + (i % nb)] = G[(j0 + i / nb) * ld + j0 + (i % nb)];
+        X[(i / nb) * ldl + (i % nb)] = 0.0;
+    }
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    const double md = *maxdiag;
+    for (int j = 0; j < nb; ++j) {
+        const double d = A[j * ldl + j];
+        if (!(d > cutoff * md)) {
+            if (tid == 0) bad = 1;
+        }
+        __syncthreads();
+        if (bad) break;
+        const double r = sqrt(d);
+        for (int c = j + tid; c < nb; c += 256) A[j * ldl + c] = (c == j) ? r : A[j * ldl + c] / r;
+        __syncthreads();
+        const int t = nb - j - 1;
+        for (int e = tid; e < t * t; e += 256) {
+            const int i = j + 1 + e / t, c = j + 1 + e % t;
+            if (c >= i) A[i * ldl + c] -= A[j * ldl + i] * A[j * ldl + c];
+        }
+        __syncthreads();
+    }
+    if (bad) {
+        if (tid == 0) *fail = 1;
+        return;
+    }
+    for (int c = tid; c < nb; c += 256) {  // back substitution, one column of R_jj^-1 per thread
+        X[c * ldl + c] = 1.0 / A[c * ldl + c];
+        for (int i = c - 1; i >= 0; --i) {
+            double acc = 0.0;
+            for (int k = i + 1; k <= c; ++k) acc += A[i * ldl + k] * X[k * ldl + c];
+            X[i * ldl + c] = -acc / A[i * ldl + i];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nb * nb; i += 256) {
+        const int r = i / nb, c = i % nb;
+        G[(j0 + r) * ld + j0 + c] = (c >= r) ? A[r * ldl + c] : 0.0;
+        Dinv[r * nb + c] = X[r * ldl + c];
+    }
+}
+
+__global__ void max_diag_kernel(const double* __restrict__ G, int64_t m, double* __restrict__ out, int* __restrict__ fail) {
+    __shared__ double red[256];
+    double v = 0.0;
+    bool nan = false;
+    for (int64_t i = threadIdx.x; i < m; i += 256) {
+        const double g = G[i * m + i];
+        if (!(g == g) || isinf(g)) nan = true;
+        v = fmax(v, g);
+    }
+    red[threadIdx.x] = nan ? -1.0 : v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double b = 0.0;
+        bool anynan = false;
+        for (int i = 0; i < 256; ++i) {
+            if (red[i] < 0.0) anynan = true;
+            b = fmax(b, red[i]);
+        }
+        *out = b;
+        if (anynan || !(b > 0.0)) *fail = 1;
+    }
+}
+
+// zero the strictly lower triangle of the m x m matrix (panel rows below the diagonal blocks are never written)
+__global__ void zero_lower_kernel(double* __restrict__ G, int64_t m) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= m * m) return;
+    if (idx / m > idx % m) G[idx] = 0.0;
+}
+
+// dst[r][c] = src^T: small transposed copy of an nb x nb block
+__global__ void transpose_block_kernel(const double* __restrict__ src, int nb, double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb * nb) dst[(i % nb) * nb + (i / nb)] = src[i];
+}
+
+// C[da x db] (+/-)= A^T B through the existing Gram kernels (rows = n): the trailing update of the Cholesky
+inline void atb_scaled(petal_ctx* ctx, const double* A, int64_t lda, int64_t da, const double* B, int64_t ldb, int64_t db,
+                       int64_t n, double* C, int64_t ldc, bool symmetric, double scale) {
+    AtbParams<double> p{};
+    p.A = A; p.lda = lda; p.da = da; p.B = B; p.ldb = ldb; p.db = db; p.n = n; p.C = C; p.ldc = ldc;
+    p.symmetric = symmetric ? 1 : 0;
+    p.negate = scale < 0.0 ? 1 : 0;
+    launch_atb<double>(ctx, p);
+}
+
+// G [m x m] in/out (R in the upper triangle), P [m x m] out (R^-1), fail: device int (must be zero on entry)
+inline void chol_blocked(petal_ctx* ctx, double* G, int64_t m, double cutoff, double* P, int* fail) {
+    KTimer kt(ctx, "cholesky_blocked", 0.0);
+    ensure_dynamic_smem(ctx, chol_diag_kernel, kCholDiagSmem);
+    DBuf<double> maxd(ctx, 1), Dinv(ctx, (size_t)(kCholNB * kCholNB)), DinvT(ctx, (size_t)(kCholNB * kCholNB));
+    max_diag_kernel<<<1, 256, 0, ctx->stream>>>(G, m, maxd.p, fail);
+    check_launch(ctx);
+    PETAL_CUDA(cudaMemsetAsync(P, 0, (size_t)(m * m) * sizeof(double), ctx->stream));
+    DBuf<double> T1(ctx, (size_t)(m * kCholNB));  // workspace for the inverse's block column
+    for (int64_t j0 = 0; j0 < m; j0 += kCholNB) {
+        const int nb = (int)std::min<int64_t>(kCholNB, m - j0);
+        chol_diag_kernel<<<1, 256, kCholDiagSmem, ctx->stream>>>(G, m, j0, nb, cutoff, maxd.p, Dinv.p, fail);
+        check_launch(ctx);
+        const int64_t rest = m - j0 - nb;
+        if (rest > 0) {
+            // R12 = R11^-T G12  (nb x rest): small GEMM with A = (R11^-1)^T
+            transpose_block_kernel<<<(unsigned)ceil_div(nb * nb, 256), 256, 0, ctx->stream>>>(Dinv.p, nb, DinvT.p);
+            check_launch(ctx);
+            DBuf<double> R12(ctx, (size_t)(nb * rest));
+            gemm_nn(ctx, DinvT.p, nb, G + j0 * m + j0 + nb, m, R12.p, rest, nb, rest, nb);
+            PETAL_CUDA(cudaMemcpy2DAsync(G + j0 * m + j0 + nb, (size_t)m * sizeof(double), R12.p, (size_t)rest * sizeof(double),
+                                         (size_t)rest * sizeof(double), (size_t)nb, cudaMemcpyDeviceToDevice, ctx->stream));
+            // G22 -= R12^T R12 (upper tiles only)
+            atb_scaled(ctx, R12.p, rest, rest, R12.p, rest, rest, nb, G + (j0 + nb) * m + j0 + nb, m, true, -1.0);
+        }
+        // inverse: P[J, J] = R11^-1;  P[0:j0, J] = -P[0:j0, 0:j0] R[0:j0, J] R11^-1
+        PETAL_CUDA(cudaMemcpy2DAsync(P + j0 * m + j0, (size_t)m * sizeof(double), Dinv.p, (size_t)nb * sizeof(double),
+                                     (size_t)nb * sizeof(double), (size_t)nb, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (j0 > 0) {
+            // T1 [j0 x nb] = P[0:j0, 0:j0] (upper) * R[0:j0, J]
+            gemm_nn(ctx, P, m, G + j0, m, T1.p, nb, j0, nb, j0, 1.0, false, /*a_upper=*/true);
+            // P[0:j0, J] = -T1 * R11^-1
+            gemm_nn(ctx, T1.p, nb, Dinv.p, nb, P + j0, m, j0, nb, nb, -1.0);
+        }
+    }
+    zero_lower_kernel<<<(unsigned)ceil_div(m * m, 256), 256, 0, ctx->stream>>>(G, m);
+    check_launch(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// block Jacobi
+// ------------------------------------------------------------------------------------------
+constexpr int kBJ = 32;          // rows per block
+constexpr int kBJ2 = 2 * kBJ;    // rows per pair
+
+__device__ __forceinline__ int64_t bj_row(int I, int J, int i) { return (i < kBJ) ? (int64_t)I * kBJ + i : (int64_t)J * kBJ + (i - kBJ); }
+
+// Gp[pair][64][64] += A_p A_p^T over this CTA's K range.  grid = (pairs, ksplit).  8 warps, warp w owns tile row w.
+__global__ void __launch_bounds__(256)
+bj_gram_kernel(const double* __restrict__ M, int64_t len, int nblk, int step, int64_t kchunk, double* __restrict__ Gp) {
+    constexpr int KC = 32, LD = KC + 4;
+    __shared__ __align__(16) double T[kBJ2 * LD];
+    int I, J;
+    rr_pair(nblk, step, blockIdx.x, I, J);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kq = lane & 3, rq = lane >> 2;
+    const int64_t k_lo = (int64_t)blockIdx.y * kchunk, k_hi = min(len, k_lo + kchunk);
+    double acc[8][2];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[b][0] = acc[b][1] = 0.0;
+    // staging: 64 rows x 32 columns = 2048 doubles -> 8 per thread: row = tid / 4, 8 consecutive columns
+    const int sr = tid >> 2, sc = (tid & 3) * 8;
+    const double* src = M + bj_row(I, J, sr) * len;
+    double st[8];
+    auto load = [&](int64_t k0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t k = k0 + sc + j;
+            st[j] = (k < k_hi) ? src[k] : 0.0;
+        }
+    };
+    auto store = [&]() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) T[sr * LD + sc + j] = st[j];
+    };
+    if (k_lo < k_hi) {
+        load(k_lo);
+        store();
+    }
+    __syncthreads();
+    for (int64_t k0 = k_lo; k0 < k_hi; k0 += KC) {
+        const bool has_next = (k0 + KC) < k_hi;
+        if (has_next) load(k0 + KC);
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; ++k4) {
+            const double a = T[(warp * 8 + rq) * LD + k4 * 4 + kq];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) dmma_m8n8k4(acc[b][0], acc[b][1], a, T[(b * 8 + rq) * LD + k4 * 4 + kq]);
+        }
+        __syncthreads();
+        if (has_next) {
+            store();
+            __syncthreads();
+        }
+    }
+    double* g = Gp + (size_t)blockIdx.x * kBJ2 * kBJ2;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        atomicAdd(&g[(warp * 8 + rq) * kBJ2 + b * 8 + 2 * kq], acc[b][0]);
+        atomicAdd(&g[(warp * 8 + rq) * kBJ2 + b * 8 + 2 * kq + 1], acc[b][1]);
+    }
+}
+
+// Per pair: off = max_{i<j} |G_ij| / sqrt(G_ii G_jj) (rows with G_ii below the zero-row floor are skipped);
+// active[pair] = off > tol; atomicMax of off into sweep_off (as ordered int bits of a non-negative double).
+__global__ void __launch_bounds__(256)
+bj_offdiag_kernel(const double* __restrict__ Gp, double tol, double zero_floor2, const double* __restrict__ amax2,
+                  int* __restrict__ active, unsigned long long* __restrict__ sweep_off) {
+    const double* g = Gp + (size_t)blockIdx.x * kBJ2 * kBJ2;
+    __shared__ double dg[kBJ2];
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    if (tid < kBJ2) dg[tid] = g[tid * kBJ2 + tid];
+    __syncthreads();
+    const double floor2 = zero_floor2 * (*amax2);
+    double best = 0.0;
+    for (int e = tid; e < kBJ2 * kBJ2; e += 256) {
+        const int i = e / kBJ2, j = e % kBJ2;
+        if (j <= i) continue;
+        const double di = dg[i], dj = dg[j];
+        if (!(di > floor2) || !(dj > floor2)) continue;
+        best = fmax(best, fabs(g[e]) * rsqrt(di * dj));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        double b = 0.0;
+        for (int w = 0; w < 8; ++w) b = fmax(b, red[w]);
+        active[blockIdx.x] = (b > tol) ? 1 : 0;
+        atomicMax(sweep_off, (unsigned long long)__double_as_longlong(b));
+    }
+}
+
+// A_p <- J_p A_p for this CTA's column chunk (128 columns).  grid = (pairs, ceil(len / 128)).  J_p [64 x 64]: rows are
+// the new orthogonal combinations.  Skipped when the pair is inactive.
+constexpr int kBJUpdCols = 128;
+constexpr int kBJUpdLDJ = kBJ2 + 4, kBJUpdLDS = kBJUpdCols + 4;
+constexpr size_t kBJUpdSmem = (size_t)(kBJ2 * kBJUpdLDJ + kBJ2 * kBJUpdLDS) * sizeof(double);
+
+__global__ void __launch_bounds__(256)
+bj_update_kernel(double* __restrict__ M, int64_t len, int nblk, int step, const double* __restrict__ Jp,
+                 const int* __restrict__ active) {
+    if (!active[blockIdx.x]) return;
+    extern __shared__ double bsm[];
+    double* Js = bsm;                          // [64][68]
+    double* S = bsm + kBJ2 * kBJUpdLDJ;        // [64][132]
+    int I, J;
+    rr_pair(nblk, step, blockIdx.x, I, J);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, kq = lane & 3, rq = lane >> 2;
+    const int64_t c0 = (int64_t)blockIdx.y * kBJUpdCols;
+    const double* jp = Jp + (size_t)blockIdx.x * kBJ2 * kBJ2;
+    for (int e = tid; e < kBJ2 * kBJ2; e += 256) Js[(e / kBJ2) * kBJUpdLDJ + (e % kBJ2)] = jp[e];
+    for (int e = tid; e < kBJ2 * kBJUpdCols; e += 256) {
+        const int r = e / kBJUpdCols, c = e % kBJUpdCols;
+        S[r * kBJUpdLDS + c] = (c0 + c < len) ? M[bj_row(I, J, r) * len + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    double acc[16][2];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) acc[b][0] = acc[b][1] = 0.0;
+#pragma unroll 4
+    for (int k4 = 0; k4 < kBJ2 / 4; ++k4) {
+        const double a = Js[(warp * 8 + rq) * kBJUpdLDJ + k4 * 4 + kq];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) dmma_m8n8k4(acc[b][0], acc[b][1], a, S[(k4 * 4 + kq) * kBJUpdLDS + b * 8 + rq]);
+    }
+    const int64_t row = bj_row(I, J, warp * 8 + rq);
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const int64_t c = c0 + b * 8 + 2 * kq;
+        if (c < len) M[row * len + c] = acc[b][0];
+        if (c + 1 < len) M[row * len + c + 1] = acc[b][1];
+    }
+}
+
+// Batched 64 x 64 two-sided Jacobi on G_p = A_p A_p^T: the orthogonal J_p with J_p G_p J_p^T diagonal.
+// A rotation of rows (p, q) of A_p depends only on G_pp, G_qq, G_pq, so this is the scalar one-sided Jacobi on the 64
+// rows of A_p carried out on their Gram matrix (G <- J G J^T) instead of on the rows themselves; the rows are
+// rotated once, afterwards, by one GEMM with the accumulated J_p.  The rotation test is the scale-invariant
+// |G_pq| > tol sqrt(G_pp G_qq) of one-sided Jacobi - the computed Gram entries are accurate relative to
+// sqrt(G_pp G_qq), so rows of very different norms are resolved (an eigen-solver with an absolute noise floor
+// eps * lambda_max, as first tried, stalls at cos ~ eps * sigma_max / sigma_min).
+// One CTA per pair, 512 threads = 32 groups of 16 lanes (one per row pair of a round-robin step); G and J live in
+// shared memory with a row pitch of 65 (the column phase walks a column: conflict-free).
+constexpr int kBJEigThreads = 512;
+constexpr int kBJEigLD = kBJ2 + 1;
+__global__ void __launch_bounds__(kBJEigThreads)
+bj_eig_kernel(const double* __restrict__ Gp, double* __restrict__ Jp, const int* __restrict__ active, int max_sweeps,
+              double tol, double zero_floor2, const double* __restrict__ amax2) {
+    if (!active[blockIdx.x]) return;
+    constexpr int m = kBJ2, LD = kBJEigLD;
+    extern __shared__ double esm[];
+    double* Gs = esm;
+    double* Js = esm + m * LD;
+    __shared__ int rotated;
+    const double* A = Gp + (size_t)blockIdx.x * m * m;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < m * m; i += kBJEigThreads) {
+        const int r = i / m, c = i % m;
+        // symmetrise on load: the two halves of the Gram differ by the rounding of differently ordered sums
+        Gs[r * LD + c] = (c >= r) ? A[i] : A[c * m + r];
+        Js[r * LD + c] = (r == c) ? 1.0 : 0.0;
+    }
+    if (tid == 0) rotated = 0;
+    __syncthreads();
+    const double floor2 = zero_floor2 * (*amax2);
+    const int gid = tid >> 4, gl = tid & 15;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        for (int step = 0; step < m - 1; ++step) {
+            int p, q;
+            rr_pair(m, step, gid, p, q);
+            const double al = Gs[p * LD + p], be = Gs[q * LD + q], ga = Gs[p * LD + q];
+            double c = 1.0, sn = 0.0;
+            bool rot = false;
+            if (al > floor2 && be > floor2 && fabs(ga) > tol * sqrt(al * be)) {
+                const double zeta = (be - al) / (2.0 * ga);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                c = rsqrt(1.0 + t * t);
+                sn = c * t;
+                rot = true;
+            }
+            __syncthreads();  // every group has read its (al, be, ga) before rows change
+            if (rot) {
+                for (int e = gl; e < m; e += 16) {  // rows p, q of G and of J
+                    const double x = Gs[p * LD + e], y = Gs[q * LD + e];
+                    Gs[p * LD + e] = c * x - sn * y;
+                    Gs[q * LD + e] = sn * x + c * y;
+                    const double jx = Js[p * LD + e], jy = Js[q * LD + e];
+                    Js[p * LD + e] = c * jx - sn * jy;
+                    Js[q * LD + e] = sn * jx + c * jy;
+                }
+                if (gl == 0) rotated = 1;
+            }
+            __syncthreads();
+            if (rot) {
+                for (int e = gl; e < m; e += 16) {  // columns p, q of G
+                    const double x = Gs[e * LD + p], y = Gs[e * LD + q];
+                    Gs[e * LD + p] = c * x - sn * y;
+                    Gs[e * LD + q] = sn * x + c * y;
+                }
+            }
+            __syncthreads();
+            if (rot && gl == 0) {
+                Gs[p * LD + q] = 0.0;  // annihilated exactly
+                Gs[q * LD + p] = 0.0;
+            }
+        }
+        __syncthreads();
+        const int r = rotated;
+        __syncthreads();
+        if (tid == 0) rotated = 0;
+        __syncthreads();
+        if (!r) break;
+    }
+    // (an inner solve that ran out of sweeps still hands back an exactly orthogonal J: the outer iteration continues)
+    double* out = Jp + (size_t)blockIdx.x * m * m;
+    for (int i = tid; i < m * m; i += kBJEigThreads) out[i] = Js[(i / m) * LD + (i % m)];
+}
+
+constexpr size_t kBJEigSmem = (size_t)(2 * kBJ2 * kBJEigLD) * sizeof(double);
+
+__global__ void bj_amax2_kernel(const double* __restrict__ nrm, int m, double* __restrict__ amax2) {
+    double a = 0.0;
+    for (int j = 0; j < m; ++j) a = fmax(a, nrm[j]);
+    *amax2 = a * a;
+}
+
+// One-sided block Jacobi on the rows of A [m x len] (device, f64, not modified).  Same contract as jacobi_rows:
+// Aout = diag(sig) N (rows sorted by sig descending), Jt optional (m x m), sig [m].
+inline void block_jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, double* Aout, double* Jt, double* sig,
+                              double input_noise_rel) {
+    KTimer kt(ctx, "jacobi_block", 0.0);
+    const int64_t mp = ceil_div(m, kBJ2) * kBJ2;  // padded with zero rows to an even number of blocks
+    const int nblk = (int)(mp / kBJ);
+    const int npairs = nblk / 2;
+    DBuf<double> M(ctx, (size_t)(mp * len)), Jm;
+    PETAL_CUDA(cudaMemsetAsync(M.p, 0, (size_t)(mp * len) * sizeof(double), ctx->stream));
+    PETAL_CUDA(cudaMemcpyAsync(M.p, A, (size_t)(m * len) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (Jt) {
+        Jm.alloc(ctx, (size_t)(mp * mp));
+        set_identity_kernel<<<(unsigned)ceil_div(mp * mp, 256), 256, 0, ctx->stream>>>(Jm.p, mp);
+        check_launch(ctx);
+    }
+    DBuf<double> nrm(ctx, (size_t)mp), amax2(ctx, 1);
+    row_norm_kernel<<<(unsigned)mp, 256, 0, ctx->stream>>>(M.p, (int)mp, (int)len, nrm.p);
+    check_launch(ctx);
+    bj_amax2_kernel<<<1, 1, 0, ctx->stream>>>(nrm.p, (int)mp, amax2.p);
+    check_launch(ctx);
+    DBuf<double> Gp(ctx, (size_t)npairs * kBJ2 * kBJ2), Jp(ctx, (size_t)npairs * kBJ2 * kBJ2);
+    DBuf<int> active(ctx, (size_t)npairs);
+    DBuf<unsigned long long> sweep_off(ctx, 1);
+    ensure_dynamic_smem(ctx, bj_update_kernel, kBJUpdSmem);
+    ensure_dynamic_smem(ctx, bj_eig_kernel, kBJEigSmem);
+    int max_sweeps = 40;
+    if (const char* e = getenv("PETAL_JACOBI_MAX_SWEEPS")) max_sweeps = std::max(1, atoi(e));
+    const double tol = 8.0 * 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
+    const double inner_tol = 8.0 * 2.220446049250313e-16 * std::sqrt((double)kBJ2);
+    // rows below the input's own noise level (eps * lambda_max for a Gram matrix) count as zero rows
+    const double zfloor = std::max(kJacobiZeroRow, input_noise_rel);
+    const double zero2 = zfloor * zfloor;
+    int ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(len, 256), (2 * ctx->sm_count) / std::max(npairs, 1)));
+    const int64_t kchunk = ceil_div(ceil_div(len, ksplit), 32) * 32;
+    ksplit = (int)ceil_div(len, kchunk);
+    const unsigned ucols = (unsigned)ceil_div(len, kBJUpdCols), jcols = (unsigned)ceil_div(mp, kBJUpdCols);
+    const bool info = getenv("PETAL_JACOBI_INFO") != nullptr;
+    bool converged = false;
+    for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+        sweep_off.zero();
+        for (int step = 0; step < nblk - 1; ++step) {
+            Gp.zero();
+            bj_gram_kernel<<<dim3((unsigned)npairs, (unsigned)ksplit), 256, 0, ctx->stream>>>(M.p, len, nblk, step, kchunk, Gp.p);
+            check_launch(ctx);
+            bj_offdiag_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(Gp.p, tol, zero2, amax2.p, active.p, sweep_off.p);
+            check_launch(ctx);
+            bj_eig_kernel<<<(unsigned)npairs, kBJEigThreads, kBJEigSmem, ctx->stream>>>(Gp.p, Jp.p, active.p, 30, inner_tol, zero2,
+                                                                                         amax2.p);
+            check_launch(ctx);
+            bj_update_kernel<<<dim3((unsigned)npairs, ucols), 256, kBJUpdSmem, ctx->stream>>>(M.p, len, nblk, step, Jp.p, active.p);
+            check_launch(ctx);
+            if (Jt) {
+                bj_update_kernel<<<dim3((unsigned)npairs, jcols), 256, kBJUpdSmem, ctx->stream>>>(Jm.p, mp, nblk, step, Jp.p, active.p);
+                check_launch(ctx);
+            }
+        }
+        unsigned long long hbits = 0;
+        PETAL_CUDA(cudaMemcpyAsync(&hbits, sweep_off.p, sizeof hbits, cudaMemcpyDeviceToHost, ctx->stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        double off;
+        std::memcpy(&off, &hbits, sizeof off);
+        if (info) fprintf(stderr, "[jacobi_block] m %lld len %lld sweep %d max off-diagonal cosine %.3e (tol %.1e)\n", (long long)m, (long long)len, sweep + 1, off, tol);
+        if (!(off > tol)) converged = true;  // the sweep found every pair already orthogonal
+        if (off != off) linalg_error("did not converge");
+    }
+    if (!converged) linalg_error("did not converge");  // src/linalg.rs:84,115
+    row_norm_kernel<<<(unsigned)mp, 256, 0, ctx->stream>>>(M.p, (int)mp, (int)len, nrm.p);
+    check_launch(ctx);
+    // sort the mp rows (padding rows have norm 0 and sort last), keep the first m
+    DBuf<double> As(ctx, Aout ? (size_t)(mp * len) : 0), Js(ctx, Jt ? (size_t)(mp * mp) : 0), ss(ctx, (size_t)mp);
+    sort_scatter_kernel<<<(unsigned)mp, 256, 0, ctx->stream>>>(M.p, Jt ? Jm.p : nullptr, nrm.p, (int)mp, (int)len, Aout ? As.p : nullptr,
+                                                              Jt ? Js.p : nullptr, ss.p);
+    check_launch(ctx);
+    if (Aout) PETAL_CUDA(cudaMemcpyAsync(Aout, As.p, (size_t)(m * len) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (Jt)  // m leading rows, m leading columns of the padded J (padding rows / columns stay decoupled: zero rows never rotate)
+        PETAL_CUDA(cudaMemcpy2DAsync(Jt, (size_t)m * sizeof(double), Js.p, (size_t)mp * sizeof(double), (size_t)m * sizeof(double),
+                                     (size_t)m, cudaMemcpyDeviceToDevice, ctx->stream));
+    PETAL_CUDA(cudaMemcpyAsync(sig, ss.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+}
+
+// ------------------------------------------------------------------------------------------
+// FP64 tensor-pipe probe: back-to-back DMMAs from registers (no memory traffic), 8 warps per CTA, 2 CTAs per SM.
+// Returns nothing; the host times it with events.  Used to anchor the "fraction of FP64 tensor peak" figures.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_probe_kernel(double* out, int iters, double seed) {
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double a = seed + threadIdx.x * 1e-9, b = seed * 0.5 + threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma_m8n8k4(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 1.2345e-300) out[0] = s;  // keeps the loop alive
+}
+
+}  // namespace petal

@@ -121,7 +121,11 @@ __global__ void ica_g_probe_kernel(float* __restrict__ U, int64_t n, int64_t nc,
 constexpr int kTraceTiles = 64;
 constexpr int kTraceEv = 16;
 __device__ __forceinline__ void ica_trace(const IcaParams& p, int ev, uint32_t it) {
+#ifdef PETAL_TC_TRACE_BUILD
     if (p.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceTiles) p.trace[ev * kTraceTiles + it] = clock64();
+#else
+    (void)p; (void)ev; (void)it;
+#endif
 }
 
 // Software pipeline (tile index t per CTA; tensor pipe order M1(0), M1(1), M2(0), M1(2), M2(1), ...):

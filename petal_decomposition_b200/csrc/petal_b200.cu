@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "small_linalg.cuh"
 #include "stream_kernels.cuh"
+#include "dense_f64.cuh"
 #include "tc_kernels.cuh"
 #include "ica_kernels.cuh"
 
@@ -410,13 +411,67 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
     ColMean<T> cm;
     compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
 
-    // Gram of the centred data; its eigen-decomposition G = V diag(sigma^2) V^T gives what the
-    // reference takes from gesvd (src/pca.rs:216-220): sigma and Vt.  The n x n U is never formed.
+    // sigma and Vt of the centred data (what the reference takes from gesvd, src/pca.rs:216-220); the n x n U is
+    // never formed.
+    //  f64: CholeskyQR2 of Xc - pass 1: G1 = Xc^T Xc, R1 = chol(G1); pass 2: G2 = (Xc R1^-1)^T (Xc R1^-1) with the
+    //       triangular solve applied on the fly chunk by chunk, R2 = chol(G2); R = R2 R1 - followed by a one-sided
+    //       Jacobi SVD of R (rows): singular values to eps * sigma_1 like a backward-stable SVD of Xc, instead of the
+    //       eps * sigma_1^2 / sigma_j a Gram eigen-decomposition gives.  Rank-deficient data (a Cholesky pivot
+    //       below 1e-12 of the largest diagonal entry, or fewer rows than columns) takes the second route.
+    //  f32, and the fallback: eigen-decomposition of G1 (f64 accumulation: far inside the f32 tolerance).
     DBuf<double> G(ctx, (size_t)(d * d)), Jt(ctx, (size_t)(d * d)), lam(ctx, (size_t)d), tvd(ctx, 1);
     centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
     trace_kernel<<<1, 256, 0, ctx->stream>>>(G.p, d, tvd.p);  // sum of all sigma^2, src/pca.rs:224
     launch1(ctx);
-    jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p, kGramNoise);
+    bool have_sigma = false;  // lam holds sigma (true) or sigma^2 (false)
+    if constexpr (sizeof(T) == 8) {
+        bool qr2 = n_total > d && d >= 2;
+        if (const char* e = getenv("PETAL_PCA_QR2")) qr2 = qr2 && atoi(e) != 0;
+        if (qr2) {
+            const double piv = 1e-12;
+            DBuf<double> R1(ctx, (size_t)(d * d)), P1(ctx, (size_t)(d * d));
+            DBuf<int> fail(ctx, 1);
+            fail.zero();
+            PETAL_CUDA(cudaMemcpyAsync(R1.p, G.p, (size_t)(d * d) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            chol_blocked(ctx, R1.p, d, piv, P1.p, fail.p);
+            int hfail = 0;
+            PETAL_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!hfail) {
+                // pass 2: Q1 = Xc P1 in row chunks (workspace <= 1 GiB), G2 += Q1^T Q1
+                DBuf<double> G2(ctx, (size_t)(d * d));
+                G2.zero();
+                int64_t rows_c = std::max<int64_t>(128, ((int64_t)1 << 30) / (d * (int64_t)sizeof(double)));
+                rows_c = std::min<int64_t>(std::max<int64_t>(n, 1), (rows_c / 128) * 128);
+                DBuf<double> Q1(ctx, (size_t)(rows_c * d));
+                for (int64_t r0 = 0; r0 < n; r0 += rows_c) {
+                    const int64_t rows = std::min<int64_t>(rows_c, n - r0);
+                    gemm_nn(ctx, reinterpret_cast<const double*>(X.p) + r0 * d, d, P1.p, d, Q1.p, d, rows, d, d, 1.0, false, false,
+                            /*b_upper=*/true, false, reinterpret_cast<const double*>(cm.mu));
+                    AtbParams<double> ap{};
+                    ap.A = Q1.p; ap.lda = d; ap.da = d; ap.B = Q1.p; ap.ldb = d; ap.db = d; ap.n = rows; ap.C = G2.p; ap.ldc = d;
+                    ap.symmetric = 1;
+                    launch_atb<double>(ctx, ap);
+                }
+                allreduce_sum(ctx, G2.p, (size_t)(d * d));
+                launch_symmetrize(ctx, G2.p, d);
+                DBuf<double> P2(ctx, (size_t)(d * d));
+                chol_blocked(ctx, G2.p, d, 1e-6, P2.p, fail.p);  // G2 ~ I: anything near-singular here means round 1 failed
+                PETAL_CUDA(cudaMemcpyAsync(&hfail, fail.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+                if (!hfail) {
+                    // R = R2 R1 (upper x upper), then SVD of R by one-sided Jacobi on its rows: R = U diag(s) N, N = Vt
+                    DBuf<double> R(ctx, (size_t)(d * d)), Aout(ctx, (size_t)(d * d));
+                    R.zero();
+                    gemm_nn(ctx, G2.p, d, R1.p, d, R.p, d, d, d, d, 1.0, false, /*a_upper=*/true, /*b_upper=*/true, /*c_upper=*/true);
+                    jacobi_rows(ctx, R.p, d, d, Aout.p, nullptr, lam.p);
+                    launch_normalize_rows(ctx, Aout.p, lam.p, d, d, 0.0, Jt.p);
+                    have_sigma = true;
+                }
+            }
+        }
+    }
+    if (!have_sigma) jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p, kGramNoise);
 
     DBuf<T> comps_tmp;
     T* comps_dev = comps.p;
@@ -438,8 +493,12 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
         gemm_xb<T>(ctx, X.p, d, n, d, comps_dev, d, true, k, cm.mu, nullptr, scores_dev, k);
         flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores);
         if (sing) {
-            sqrt_cast_kernel<T><<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(lam.p, k, sing.p);
-            launch1(ctx);
+            if (have_sigma) {
+                launch_cast<double, T>(ctx, lam.p, sing.p, k);
+            } else {
+                sqrt_cast_kernel<T><<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(lam.p, k, sing.p);
+                launch1(ctx);
+            }
         }
     }
     if (mean) launch_cast<T, T>(ctx, cm.mean_t.p, mean.p, d);
@@ -1576,6 +1635,30 @@ int petal_small_svd_f64(petal_ctx* ctx, const double* a, int64_t m, int64_t len,
         S.commit(ctx);
         Vt.commit(ctx);
         finish_call(ctx, U.to_host || S.to_host || Vt.to_host);
+    });
+}
+
+int petal_probe_dmma_tflops(petal_ctx* ctx, int ctas_per_sm, double* out) {
+    return guarded(ctx, [&] {
+        if (!out || ctas_per_sm < 1 || ctas_per_sm > 8) invalid_input("bad probe arguments");
+        DBuf<double> sink(ctx, 1);
+        const int iters = 1 << 14, grid = ctx->sm_count * ctas_per_sm;
+        cudaEvent_t a, b;
+        PETAL_CUDA(cudaEventCreate(&a));
+        PETAL_CUDA(cudaEventCreate(&b));
+        dmma_probe_kernel<<<grid, 256, 0, ctx->stream>>>(sink.p, 256, 1.0);  // warm-up
+        launch1(ctx);
+        PETAL_CUDA(cudaEventRecord(a, ctx->stream));
+        dmma_probe_kernel<<<grid, 256, 0, ctx->stream>>>(sink.p, iters, 1.0);
+        launch1(ctx);
+        PETAL_CUDA(cudaEventRecord(b, ctx->stream));
+        PETAL_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        PETAL_CUDA(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        const double flops = (double)grid * 8.0 * iters * 16.0 * 512.0;
+        *out = flops / (ms * 1e-3) / 1e12;
     });
 }
 

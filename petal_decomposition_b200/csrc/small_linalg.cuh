@@ -64,6 +64,11 @@ __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, doubl
     return true;
 }
 
+// Rows whose norm is below kJacobiZeroRow * (largest row norm) are numerically zero (rank-deficient inputs: m > len,
+// repeated samples): their direction is rounding noise, rotating them never terminates, and what they are rotated
+// against does not change beyond eps.  They take part in no rotation.
+constexpr double kJacobiZeroRow = 4.0 * 2.220446049250313e-16;
+
 // ------------------------------------------------------------------------------------------
 // single-CTA engine
 // ------------------------------------------------------------------------------------------
@@ -103,7 +108,7 @@ jacobi_smem_kernel(const double* __restrict__ A, int m, int len, double* __restr
     __syncthreads();
     double amax = 0.0;
     for (int j = 0; j < m; ++j) amax = fmax(amax, nrm[j]);
-    const double noise = noise_rel * sqrt(amax);
+    const double noise = fmax(noise_rel, kJacobiZeroRow) * sqrt(amax);
     __syncthreads();
 
     const int me = (m + 1) & ~1;
@@ -317,7 +322,7 @@ jacobi_coop_kernel(double* __restrict__ M, int m, int len, double* __restrict__ 
             amax = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) amax = fmax(amax, red[w]);
-            noise = noise_rel * sqrt(amax);
+            noise = fmax(noise_rel, kJacobiZeroRow) * sqrt(amax);
         }
         for (int step = 0; step < me - 1; ++step) {
             for (int pi = blockIdx.x; pi < me / 2; pi += gridDim.x) {
@@ -393,7 +398,7 @@ row_norm_kernel(const double* __restrict__ M, int m, int len, double* __restrict
 __global__ void noise_floor_kernel(const double* __restrict__ nrm, int m, double noise_rel, double* __restrict__ noise) {
     double a = 0.0;
     for (int j = 0; j < m; ++j) a = fmax(a, nrm[j]);
-    noise[0] = noise_rel * a;
+    noise[0] = fmax(noise_rel, kJacobiZeroRow) * a;
 }
 
 __global__ void __launch_bounds__(256)
@@ -425,6 +430,14 @@ sort_scatter_kernel(const double* __restrict__ M, const double* __restrict__ J,
 // Jt[m][m] (may be null), sig[m].  Returns the number of sweeps used (-1 if unknown).
 // input_noise_rel: relative entry noise of A (0 for an exactly given matrix; ~eps for a Gram matrix
 // accumulated in f64) - sets the orthogonality floor, see jacobi_rotation.
+// block engine for large m (dense_f64.cuh)
+inline void block_jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, double* Aout, double* Jt, double* sig,
+                              double input_noise_rel);
+inline int64_t jacobi_block_min() {
+    if (const char* e = getenv("PETAL_JACOBI_BLOCK_MIN")) return std::max<int64_t>(2, atoll(e));
+    return 2048;
+}
+
 inline bool jacobi_fits_smem(int64_t m, int64_t len) {
     return ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double) <= 200 * 1024;
 }
@@ -444,6 +457,11 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     const double tol = 8.0 * 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
     size_t smem = ((size_t)m * len + (size_t)m * m + (size_t)m) * sizeof(double);
     const bool use_smem = !force_global && smem <= 200 * 1024;
+    if (!use_smem && run_flag == nullptr && m >= jacobi_block_min()) {
+        // rotations as DMMA GEMMs on pairs of 32-row blocks: the scalar engines below are DFMA-issue bound
+        block_jacobi_rows(ctx, A, m, len, Aout, Jt, sig, input_noise_rel);
+        return -1;
+    }
     KTimer kt(ctx, use_smem ? "jacobi_smem" : "jacobi_global", 0.0);
     ctx->status_armed = true;
     if (use_smem) {

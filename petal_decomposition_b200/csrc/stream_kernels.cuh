@@ -322,6 +322,7 @@ struct AtbParams {
     int64_t ldc;
     int symmetric;  // A == B: compute tiles with tile_j >= tile_i only (mirror afterwards)
     int tiles_j;
+    int negate;     // C -= A^T B (trailing update of the blocked Cholesky)
 };
 
 template <typename T, int TI, int TJ, bool ALIGNED>
@@ -415,7 +416,7 @@ __global__ void __launch_bounds__(256) atb_kernel(AtbParams<T> p) {
                 int64_t gj;
                 if constexpr (VEC_J) gj = j0 + (j / V) * (16 * V) + tj * V + (j % V);
                 else gj = j0 + tj + 16 * j;
-                if (gi < p.da && gj < p.db) atomicAdd(&p.C[gi * p.ldc + gj], (double)acc[i][j]);
+                if (gi < p.da && gj < p.db) atomicAdd(&p.C[gi * p.ldc + gj], p.negate ? -(double)acc[i][j] : (double)acc[i][j]);
                 acc[i][j] = T(0);
             }
         }
@@ -600,8 +601,8 @@ __global__ void __launch_bounds__(256) atb_dmma_kernel(AtbParams<double> p) {
         for (int b = 0; b < 8; ++b) {
             const int64_t gj = j0 + wj * 64 + b * 8 + 2 * kq;
             if (gi < p.da) {
-                if (gj < p.db) atomicAdd(&p.C[gi * p.ldc + gj], acc[a][b][0]);
-                if (gj + 1 < p.db) atomicAdd(&p.C[gi * p.ldc + gj + 1], acc[a][b][1]);
+                if (gj < p.db) atomicAdd(&p.C[gi * p.ldc + gj], p.negate ? -acc[a][b][0] : acc[a][b][0]);
+                if (gj + 1 < p.db) atomicAdd(&p.C[gi * p.ldc + gj + 1], p.negate ? -acc[a][b][1] : acc[a][b][1]);
             }
         }
     }

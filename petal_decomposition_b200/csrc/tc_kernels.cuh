@@ -59,10 +59,26 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded wait: a pipeline bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    long long t0 = 0;
-    for (uint32_t it = 0;; ++it) {
+// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint elapses)
+// instead of letting it spin.  A software spin loop (try_wait without hint + iteration bookkeeping) was measured
+// (ncu source page, r02) at 25-40 % of all warp instructions of the tc kernels - issue slots and power taken from the
+// transform warps that share the scheduler.  kWaitHintNs * kWaitTries bounds the wait at ~4 s.
+#ifndef PETAL_WAIT_HINT_NS
+#define PETAL_WAIT_HINT_NS 1000000
+#endif
+constexpr uint32_t kWaitHintNs = PETAL_WAIT_HINT_NS;   // 0: no hint (the hardware's default, short, suspend time)
+constexpr uint32_t kWaitTries = kWaitHintNs >= 1000u ? 4000000000u / kWaitHintNs : 40000000u;
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    if (kWaitHintNs != 0u)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(kWaitHintNs)
+            : "memory");
+    else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -70,14 +86,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(done)
             : "r"(bar), "r"(parity)
             : "memory");
-        if (done) return;
-        if (it == 64) t0 = clock64();
-        if (it > 64 && (it & 1023) == 0 && clock64() - t0 > 4000000000LL) {
-            printf("petal tc kernel: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                   threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
+    return done != 0;
+}
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+    printf("petal tc kernel: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+    for (uint32_t it = 0; it < kWaitTries; ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    mbar_timeout(bar, parity);
 }
 // non-blocking probe of a barrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
@@ -297,14 +317,35 @@ __device__ __forceinline__ uint32_t bar_full_b2(uint32_t base, int s) { return b
 // ------------------------------------------------------------------------------------------
 constexpr int kTraceKB = 512;   // K blocks traced (CTA 0 only)
 constexpr int kTraceEvents = 12;
+// timeline tracing is a build option (-DPETAL_TC_TRACE_BUILD): even a not-taken trace check costs a parameter load, a
+// special-register read and a compare per event in loops that are issue-bound
 __device__ __forceinline__ void trace_ev(const TcParams& p, int ev, uint32_t it) {
+#ifdef PETAL_TC_TRACE_BUILD
     if (p.trace != nullptr && blockIdx.x == 0 && it < (uint32_t)kTraceKB) p.trace[ev * kTraceKB + it] = clock64();
+#else
+    (void)p; (void)ev; (void)it;
+#endif
 }
 
 struct Group {
     int64_t row0;
     int64_t kblocks;
     int f0;
+};
+
+// Position in a ring of `n` stages, advanced incrementally: a runtime `it % n`, `it / n` pair costs an
+// I2F / MUFU.RCP / IMAD.HI sequence per use in loops that are issue-bound.
+struct RingPos {
+    int s = 0;
+    uint32_t ph = 0;
+    int n;
+    __device__ __forceinline__ explicit RingPos(int n_) : n(n_) {}
+    __device__ __forceinline__ void advance() {
+        if (++s == n) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
 };
 
 template <bool ATB>
@@ -615,14 +656,15 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
         };
         Group g;
         g.f0 = 0;
+        RingPos rx(S), rb(p.stages_b), ry(kYBufs);
         for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
             float mu_f = 0.f;
             if (ATB) mu_f = p.mu_pad[g.f0 + mt * 128 + lrow];
             const bool row_valid = ATB ? true : (g.row0 + mt * 128 + lrow < p.n);
             float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
-            for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
-                const int s = (int)(it % (uint32_t)S);
-                const uint32_t ph = (it / (uint32_t)S) & 1u;
+            for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it, rx.advance()) {
+                const int s = rx.s;
+                const uint32_t ph = rx.ph;
                 const uint32_t gran = 2u * it + (uint32_t)half;  // this warp's half K block
                 const int ta = (int)(gran % (uint32_t)kSlots);
                 const uint32_t pa = (gran / (uint32_t)kSlots) & 1u;
@@ -671,11 +713,13 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                     if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
                 }
                 if (ATB && !panel) {
-                    const int sb = (int)(it % (uint32_t)p.stages_b);
-                    mbar_wait(bar_full_b(bars, sb), (it / (uint32_t)p.stages_b) & 1u);  // Y tile landed
+                    const int sb = rb.s;
+                    mbar_wait(bar_full_b(bars, sb), rb.ph);  // Y tile landed
                     if (warp == 0 && lane == 0) trace_ev(p, 8, it);
-                    const int yb = (int)(it % (uint32_t)kYBufs);
-                    mbar_wait(bar_y_free(bars, yb), ((it / (uint32_t)kYBufs) & 1u) ^ 1u);  // MMAs of K block it-3 done
+                    const int yb = ry.s;
+                    mbar_wait(bar_y_free(bars, yb), ry.ph ^ 1u);  // MMAs of K block it-3 done
+                    rb.advance();
+                    ry.advance();
                     if (warp == 0 && lane == 0) trace_ev(p, 9, it);
                     {
                     // B operand of this K block: raw Y tile [32 rows][n_pad] (row-major) -> transposed
@@ -861,83 +905,63 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(base_ptr + L.tmem_slot);
 
     if (warp >= kTransformWarps) {
-        if (ATB && panel && p.b_split && (warp == kTransformWarps || warp == kTransformWarps + 3)) {
-            // ================ tc_atb with in-kernel B_lo: one TMA producer for both rings + a splitter warp ================
+        if (ATB && panel && p.b_split && warp == kTransformWarps + 3) {
+            // ================ tc_atb with in-kernel B_lo: B-ring loader + splitter warp ================
             // Only the Y panel is in HBM.  The rows of a CTA's slice are contiguous, so K block i of the CTA starts at
-            // row s0 + 32 i whatever the group structure.
-            const int fg = (int)(blockIdx.x % (unsigned)p.fgroups);
+            // row s0 + 32 i whatever the group structure.  This warp loads the panel blocks itself (lane 0, blocking
+            // waits, refilling the stage of block i-1 after block i has been split: the MMAs of block i-1 are finishing
+            // then, and SB-1 blocks stay in flight) - the earlier single producer lane polling both rings with
+            // non-blocking probes took every other issue slot of its scheduler (r02 ncu: 38 % of the kernel's warp
+            // instructions).  The X ring keeps its own producer (warp 16, below).
             const int64_t s0 = (int64_t)(blockIdx.x / (unsigned)p.fgroups) * p.slice_rows;
             const int64_t s1 = min(p.n, s0 + p.slice_rows);
             const uint32_t total = (s1 > s0) ? (uint32_t)((s1 - s0 + kKB - 1) / kKB) : 0u;
-            if (warp == kTransformWarps) {
-                // lane 0 feeds the X ring and the B ring, whichever has a free stage (non-blocking probes: the two
-                // rings are released by different consumers and must not wait for each other)
-                if (lane == 0) {
-                    uint32_t ix = 0, ib = 0, idle = 0;
-                    while (ix < total || ib < total) {
-                        bool progressed = false;
-                        if (ix < total) {
-                            const int sx = (int)(ix % (uint32_t)S);
-                            if (mbar_test(bar_empty_x(bars, sx), ((ix / (uint32_t)S) & 1u) ^ 1u)) {
-                                const uint32_t full = bar_full(bars, sx);
-                                mbar_expect_tx(full, L.stage_x);
+            auto load_block = [&](uint32_t blk, int stage) {
+                const uint32_t fullb = bar_full_b(bars, stage);
+                const int64_t r = s0 + (int64_t)blk * kKB;
+                mbar_expect_tx(fullb, L.stage_b);
+                tma_load_2d(base + L.bhi + (uint32_t)stage * L.stage_b, &p.map_bhi, 0, (int)(r / 32) * n_pad, fullb);
+            };
+            if (lane == 0)
+                for (uint32_t i = 0; i < total && i < (uint32_t)SB; ++i) load_block(i, (int)i);
+            RingPos rb(SB), rr(SB);  // block being split / stage being refilled (one block behind)
+            for (uint32_t it = 0; it < total; ++it, rb.advance()) {
+                const int sb = rb.s;
+                mbar_wait(bar_full_b(bars, sb), rb.ph);
+                // the block TMA dropped into the B ring is the B_hi operand as it is (the tensor core ignores the low
+                // mantissa bits); B_lo = y - tf32(y) is derived here, element-wise in the same swizzled layout
+                const float4* bh = reinterpret_cast<const float4*>(base_ptr + L.bhi + (uint32_t)sb * L.stage_b);
+                float4* bl = reinterpret_cast<float4*>(base_ptr + L.blo + (uint32_t)sb * L.stage_b);
+                constexpr int kPer = ATB ? (NP * 8 + 31) / 32 : 1;  // 16 B chunks per lane
+                float4 h[kPer];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    tma_load_2d(base + L.x + (uint32_t)sx * L.stage_x + (uint32_t)j * 4096u, &p.map_x,
-                                                fg * 256 + 32 * j, (int)(s0 + (int64_t)ix * kKB), full);
-                                ++ix;
-                                progressed = true;
-                            }
-                        }
-                        if (ib < total) {
-                            const int sb = (int)(ib % (uint32_t)SB);
-                            if (mbar_test(bar_empty_b(bars, sb), ((ib / (uint32_t)SB) & 1u) ^ 1u)) {
-                                const uint32_t fullb = bar_full_b(bars, sb);
-                                const int64_t r = s0 + (int64_t)ib * kKB;
-                                mbar_expect_tx(fullb, L.stage_b);
-                                tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, 0, (int)(r / 32) * n_pad, fullb);
-                                ++ib;
-                                progressed = true;
-                            }
-                        }
-                        if (progressed) {
-                            idle = 0;
-                        } else if (++idle > 400000000u) {
-                            printf("petal tc kernel: TMA producer stalled (block %d)\n", blockIdx.x);
-                            __trap();
-                        }
+                for (int u = 0; u < kPer; ++u) {
+                    const int e = lane + 32 * u;
+                    if (e < NP * 8) h[u] = bh[e];
+                }
+#pragma unroll
+                for (int u = 0; u < kPer; ++u) {
+                    const int e = lane + 32 * u;
+                    if (e < NP * 8) {
+                        float4 l4;
+                        l4.x = h[u].x - __uint_as_float(__float_as_uint(h[u].x) & 0xFFFFE000u);
+                        l4.y = h[u].y - __uint_as_float(__float_as_uint(h[u].y) & 0xFFFFE000u);
+                        l4.z = h[u].z - __uint_as_float(__float_as_uint(h[u].z) & 0xFFFFE000u);
+                        l4.w = h[u].w - __uint_as_float(__float_as_uint(h[u].w) & 0xFFFFE000u);
+                        bl[e] = l4;
                     }
                 }
-            } else {
-                // splitter: the block TMA dropped into the B ring is the B_hi operand as it is (the tensor core ignores
-                // the low mantissa bits); B_lo = y - tf32(y) is derived here, element-wise in the same swizzled layout
-                for (uint32_t it = 0; it < total; ++it) {
-                    const int sb = (int)(it % (uint32_t)SB);
-                    mbar_wait(bar_full_b(bars, sb), (it / (uint32_t)SB) & 1u);
-                    const float4* bh = reinterpret_cast<const float4*>(base_ptr + L.bhi + (uint32_t)sb * L.stage_b);
-                    float4* bl = reinterpret_cast<float4*>(base_ptr + L.blo + (uint32_t)sb * L.stage_b);
-                    constexpr int kPer = ATB ? (NP * 8 + 31) / 32 : 1;  // 16 B chunks per lane
-                    float4 h[kPer];
-#pragma unroll
-                    for (int u = 0; u < kPer; ++u) {
-                        const int e = lane + 32 * u;
-                        if (e < NP * 8) h[u] = bh[e];
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full_b2(bars, sb));
+                if (it >= 1) {
+                    const uint32_t nxt = it - 1u + (uint32_t)SB;
+                    if (nxt < total && lane == 0) {
+                        mbar_wait(bar_empty_b(bars, rr.s), rr.ph);  // MMAs of block it-1 have read the stage
+                        load_block(nxt, rr.s);
                     }
-#pragma unroll
-                    for (int u = 0; u < kPer; ++u) {
-                        const int e = lane + 32 * u;
-                        if (e < NP * 8) {
-                            float4 l4;
-                            l4.x = h[u].x - __uint_as_float(__float_as_uint(h[u].x) & 0xFFFFE000u);
-                            l4.y = h[u].y - __uint_as_float(__float_as_uint(h[u].y) & 0xFFFFE000u);
-                            l4.z = h[u].z - __uint_as_float(__float_as_uint(h[u].z) & 0xFFFFE000u);
-                            l4.w = h[u].w - __uint_as_float(__float_as_uint(h[u].w) & 0xFFFFE000u);
-                            bl[e] = l4;
-                        }
-                    }
-                    fence_proxy_async();
+                    rr.advance();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_full_b2(bars, sb));
                 }
             }
         } else if (warp == kTransformWarps) {
@@ -945,10 +969,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             if (lane == 0) {
                 uint32_t it = 0;
                 Group g;
+                RingPos rx(S);
                 for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
-                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
-                        const int s = (int)(it % (uint32_t)S);
-                        const uint32_t ph = (it / (uint32_t)S) & 1u;
+                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it, rx.advance()) {
+                        const int s = rx.s;
+                        const uint32_t ph = rx.ph;
                         mbar_wait(bar_empty_x(bars, s), ph ^ 1u);
                         trace_ev(p, 0, it);
                         const uint32_t full = bar_full(bars, s);
@@ -974,10 +999,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             if (lane == 0) {
                 uint32_t it = 0;
                 Group g;
+                RingPos rb(SB);
                 for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
-                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it) {
-                        const int sb = (int)(it % (uint32_t)SB);
-                        const uint32_t phb = (it / (uint32_t)SB) & 1u;
+                    for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it, rb.advance()) {
+                        const int sb = rb.s;
+                        const uint32_t phb = rb.ph;
                         mbar_wait(bar_empty_b(bars, sb), phb ^ 1u);
                         const uint32_t fullb = bar_full_b(bars, sb);
                         if (ATB && panel) {
@@ -1019,9 +1045,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             int abuf = 0;
             uint32_t acc = 0;
             Group g;
+            RingPos rb(SB), ry(kYBufs);
             for (int64_t gi = 0; get_group<ATB>(p, gi, g); ++gi) {
                 const int nkb = (int)g.kblocks;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                for (int kb = 0; kb < nkb; ++kb, ++it, rb.advance(), ry.advance()) {
                     bool chain_start, chain_end;
                     if constexpr (stagger) {
                         // see transform_role: this M tile's chains, buffers rotate over the chains of both M tiles
@@ -1045,8 +1072,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                             ++chains;
                         }
                     }
-                    const int sb = (int)(it % (uint32_t)SB);
-                    const uint32_t phb = (it / (uint32_t)SB) & 1u;
+                    const int sb = rb.s;
+                    const uint32_t phb = rb.ph;
                     // tc_xb reads its B tiles straight from the TMA ring; tc_atb's B tiles are TMA-loaded panels, or
                     // (row-major Y) produced by ALL transform warps - then both halves must have checked in first
                     if (!ATB || panel) mbar_wait((ATB && p.b_split) ? bar_full_b2(bars, sb) : bar_full_b(bars, sb), phb);
@@ -1057,7 +1084,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         mbar_wait(bar_a_ready(bars, (int)((2u * it + 1u) % aslots)), ((2u * it + 1u) / aslots) & 1u);
                     }
                     // B operand tiles, K-major [n_pad][32 fp32] SWIZZLE_128B
-                    const int yb = (int)(it % (uint32_t)kYBufs);
+                    const int yb = ry.s;
                     const uint32_t ring = base + L.ylo + (uint32_t)yb * L.ylo_bytes;
                     const bool from_ring = ATB && !panel;
                     const uint32_t bhi_addr = from_ring ? ring : (base + L.bhi + (uint32_t)sb * L.stage_b);

@@ -91,6 +91,82 @@ def test_c5_shape_rpca_f32_vs_oracle(pd):
     assert np.allclose(m.transform(x), y, atol=2e-3 * np.abs(y).max())
 
 
+# ------------------------------------------------------------------------------------ c4
+def test_c4_shape_pca_f64_vs_oracle(pd):
+    """configs[3] at 20 000 rows: exact Pca f64, d = 4096 - CholeskyQR2 (two DMMA Gram passes, blocked Cholesky),
+    R = R2 R1, block one-sided Jacobi SVD of R (4096 x 4096) - against the oracle's economy gesvd."""
+    n, d, k = 20_000, 4096, 64
+    import os
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_shape_20000x4096.npz"))
+    x = bench.make_x_host(n, d, "f64", "pca")
+    # the fixture is the oracle's result on exactly this matrix (tests/golden/make_c4_fixture.py; the economy gesvd of
+    # 20000 x 4096 costs minutes of CPU time, so it is not recomputed on the GPU box)
+    assert abs(float(np.sum(x[::997, ::13])) - float(fx["x_checksum"][0])) < 1e-6 * abs(float(fx["x_checksum"][0]))
+    sref_all, tv_ref, comps_ref = fx["singular"], float(fx["total_variance"][0]), fx["components16"]
+    m = pd.Pca.new(k)
+    prof = _profiled_fit(pd, m, x)
+    assert "jacobi_block" in prof and "cholesky_blocked" in prof, prof
+    assert rel(m.singular_values(), sref_all[:k]) < 1e-10
+    assert rel(m.explained_variance_ratio(), sref_all[:k] ** 2 / tv_ref) < 1e-10
+    assert abs(m._total_variance - tv_ref) < 1e-10 * tv_ref
+    assert np.allclose(m.mean(), fx["means"], atol=1e-12)
+    cm = opca.sign_normalize_rows(m.components()[:16])
+    cr = opca.sign_normalize_rows(comps_ref)
+    assert np.max(np.abs(cm - cr)) < 1e-7
+    # the whole spectrum (all 4096 singular values), not only the k reported ones
+    mfull = pd.Pca.new(d)
+    mfull.fit(x)
+    sfull = mfull.singular_values()
+    assert np.max(np.abs(sfull - sref_all)) < 1e-12 * sref_all[0]
+    assert rel(sfull, sref_all) < 1e-10
+
+
+def test_pca_f64_graded_spectrum_accuracy(pd):
+    """Singular values spread over six orders of magnitude.  A backward-stable SVD (the reference's gesvd, the
+    oracle) resolves sigma_j to ~eps * sigma_1 absolute; an eigen-decomposition of the Gram matrix only to
+    eps * sigma_1^2 / sigma_j (1e-4 relative at sigma_j = 1e-6 sigma_1).  CholeskyQR2 + Jacobi SVD of R must be in the
+    first class: every sigma_j >= 1e-6 sigma_1 within 2e-13 sigma_1 of the oracle's, and within 1e-10 relative down
+    to 1e-3 sigma_1."""
+    rng = np.random.default_rng(12)
+    n, d = 6000, 160
+    u, _ = np.linalg.qr(rng.standard_normal((n, d)))
+    v, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    s = np.logspace(0, -6, d) * 50.0
+    x = (u * s) @ v.T + rng.uniform(-1, 1, d)
+    x -= x.mean(axis=0)  # keep the constructed spectrum: centring must not mix it
+    ref = opca.Pca(d, economy=True)
+    ref.fit(x)
+    m = pd.Pca.new(d)
+    m.fit(x)
+    sg, sr = m.singular_values(), ref.singular_values()
+    assert np.max(np.abs(sg - sr)) < 2e-13 * sr[0], np.max(np.abs(sg - sr)) / sr[0]
+    big = sr > 1e-3 * sr[0]
+    assert rel(sg[big], sr[big]) < 1e-10
+    assert rel(sg, sr) < 1e-6          # eps * sigma_1 / sigma_j at the small end (the Gram route: 1e-4)
+    cm = opca.sign_normalize_rows(m.components()[big])
+    cr = opca.sign_normalize_rows(ref.components[big])
+    assert np.max(np.abs(cm - cr)) < 1e-7
+
+
+@pytest.mark.parametrize("m_,ln", [(300, 64), (2048, 2048)])
+def test_block_jacobi_svd(pd, monkeypatch, m_, ln):
+    """The block engine (pairs of 32-row blocks, DMMA Gram + 64 x 64 Jacobi + DMMA update) against LAPACK;
+    PETAL_JACOBI_BLOCK_MIN lowers its threshold so that a small ragged case (m not a multiple of 64, m > len:
+    rank-deficient rows) runs through it too."""
+    rng = np.random.default_rng(m_ + ln)
+    monkeypatch.setenv("PETAL_JACOBI_BLOCK_MIN", "256")
+    if m_ == 300:
+        a = rng.standard_normal((m_, ln)) @ np.diag(np.logspace(0, -3, ln))   # 300 x 64: padded to 320 rows, rank 64
+    else:
+        a = rng.standard_normal((m_, ln)) * np.logspace(0, -4, ln)
+    u, s, vt = pd.small_svd(a)
+    sref = np.linalg.svd(a, compute_uv=False)
+    kk = len(sref)
+    assert np.max(np.abs(s[:kk] - sref)) < 1e-12 * sref[0]
+    assert np.allclose((u[:, :kk] * s[:kk]) @ vt[:kk], a, atol=1e-11 * sref[0])
+    assert np.allclose(u.T @ u, np.eye(u.shape[0]), atol=1e-10)
+
+
 # ------------------------------------------------------------------------------------ c3
 def test_c3_shape_fastica_f32_vs_oracle(pd):
     """configs[2] at 200 000 rows: d = nc = 64 f32 - the one-pass tcgen05 kernel + the fused update kernel
@@ -121,7 +197,9 @@ def test_c3_shape_fastica_f32_vs_oracle(pd):
 def test_c3_one_pass_iterates_vs_oracle(pd, fun, name):
     """Fixed-point iterates of the one-pass tcgen05 kernel + fused update kernel (d = nc = 64, f32 data) against the
     oracle's ica_par on the SAME whitened f32 data and w_init: no whitening sign ambiguity is left, so W must agree
-    step by step to f32 accuracy."""
+    step by step to f32 accuracy.  The first steps are ill-conditioned (Gd = E[g(Wx) x^T] - diag(E g') W is a small
+    difference of O(1) terms: smallest singular value ~2e-4 here), so "f32 accuracy" is calibrated by the oracle
+    itself run in float32: the GPU path must stay within a small factor of that deviation."""
     n, d = 120_000, 64
     x, _ = synth.mixed_sources(n, d, seed=3, dtype=np.float64)
     xc = (x - x.mean(axis=0)).T
@@ -131,6 +209,8 @@ def test_c3_one_pass_iterates_vs_oracle(pd, fun, name):
     ctx = pd.default_context()
     for iters in (1, 3):
         wr, _ = oica.ica_par(x1t.T.astype(np.float64), 0.0, iters, w_init, fun=name)
+        w32, _ = oica.ica_par(np.ascontiguousarray(x1t.T), np.float32(0.0), iters, w_init.astype(np.float32), fun=name)
+        dev32 = float(np.max(np.abs(w32 - wr)))
         ctx.set_profiling(True)
         ctx.profile()
         w, ni = pd.ica_par(x1t, 0.0, iters, w_init, fun=fun)
@@ -138,7 +218,8 @@ def test_c3_one_pass_iterates_vs_oracle(pd, fun, name):
         ctx.set_profiling(False)
         assert "ica_fused_f32" in prof, prof
         assert ni == iters
-        assert np.max(np.abs(w - wr)) < 2e-5, (iters, np.max(np.abs(w - wr)))
+        err = float(np.max(np.abs(w - wr)))
+        assert err < max(5.0 * dev32, 1e-4), (iters, err, dev32)
         assert np.allclose(w @ w.T, np.eye(d), atol=1e-9)
 
 
