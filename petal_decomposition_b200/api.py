@@ -170,6 +170,17 @@ class Pcg:
         """`Pcg::from_rng(&mut rand::rng())` / `rand::rng().random()` seeds (src/pca.rs:342-347,580-583)."""
         return cls.from_seed(int.from_bytes(os.urandom(16), "little"))
 
+    def to_json_obj(self) -> dict:
+        """rand_pcg's serde form of `Mcg128Xsl64`: {"state": u128}."""
+        return {"state": self.state()}
+
+    @classmethod
+    def from_json_obj(cls, obj) -> "Pcg":
+        lib = _cabi.load()
+        st = int(obj["state"]) & ((1 << 128) - 1)
+        # the generator keeps the state verbatim (an odd value, as every constructor leaves it)
+        return cls(C.c_void_p(lib.petal_rng_from_state(st >> 64, st & ((1 << 64) - 1))))
+
     def next_u64(self) -> int:
         return int(self._lib.petal_rng_next_u64(self._h))
 
@@ -192,6 +203,38 @@ class Pcg:
                 self._h = None
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------
+# serde wire format of fitted models (reference: `#[derive(Serialize, Deserialize)]` on the model structs,
+# src/pca.rs:36-51,309-329, src/ica.rs:33-50, with ndarray's and rand_pcg's own serde impls) as serde_json
+# writes it, so that a model fitted here loads in the CPU crate and vice versa:
+#   Array2 / Array1 -> {"v": 1, "dim": [rows, cols] | [len], "data": [row-major elements]}   (ndarray array_serde)
+#   Mcg128Xsl64     -> {"state": <u128 as a JSON integer>}                                   (rand_pcg, feature serde)
+#   struct fields in declaration order; unknown fields are ignored on input like serde does by default
+#   (the reference's own test reads a RandomizedPca document into a Pca, src/pca.rs:1029-1041).
+# ---------------------------------------------------------------------------------------------
+def _json_scalar(v, dtype):
+    if np.dtype(dtype) == np.float32:
+        return float(str(np.float32(v)))  # shortest digits that round-trip as f32, like serde_json's f32 output
+    return float(v)
+
+
+def _json_array(a: np.ndarray):
+    a = np.asarray(a)
+    return {"v": 1, "dim": list(a.shape), "data": [_json_scalar(v, a.dtype) for v in a.reshape(-1)]}
+
+
+def _array_from_json(obj, dtype, ndim):
+    if not isinstance(obj, dict) or obj.get("v") != 1:
+        raise InvalidInput("unsupported ndarray serde version")
+    dim = [int(x) for x in obj["dim"]]
+    if len(dim) != ndim:
+        raise InvalidInput(f"expected a {ndim}-dimensional array")
+    data = np.asarray(obj["data"], dtype=dtype)
+    if data.size != int(np.prod(dim)):
+        raise InvalidInput("data and dimension must match in size")  # ndarray's own message
+    return np.ascontiguousarray(data.reshape(dim))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -358,6 +401,28 @@ class _PcaBase:
         self._total_variance = float(tv[0])
         self._n_samples = a.shape[0]
 
+    # ---- serde (field order of the reference structs, src/pca.rs:41-51 / 317-329) ----
+    def _json_fields(self) -> dict:
+        dt = self._components.dtype if self._components.dtype in _SUFFIX else np.dtype(np.float64)
+        return {"components": _json_array(self._components.astype(dt, copy=False)), "n_samples": int(self._n_samples),
+                "means": _json_array(np.asarray(self._means, dtype=dt)),
+                "total_variance": _json_scalar(self._total_variance, dt),
+                "singular": _json_array(np.asarray(self._singular, dtype=dt)), "centering": bool(self._centering)}
+
+    def _load_json_fields(self, obj: dict, dtype):
+        self._components = _array_from_json(obj["components"], dtype, 2)
+        self._n_samples = int(obj["n_samples"])
+        self._means = _array_from_json(obj["means"], dtype, 1)
+        self._total_variance = float(obj["total_variance"])
+        self._singular = _array_from_json(obj["singular"], dtype, 1)
+        self._centering = bool(obj["centering"])
+        self._k = self._components.shape[0]
+
+    def to_json(self) -> str:
+        """`serde_json::to_string(&model)` of the reference (tests src/pca.rs:935-947, 1029-1041)."""
+        import json
+        return json.dumps(self._json_fields(), separators=(",", ":"))
+
 
 class Pca(_PcaBase):
     """Principal component analysis - reference `Pca<A>` (src/pca.rs:41-231)."""
@@ -368,6 +433,14 @@ class Pca(_PcaBase):
     @classmethod
     def new(cls, n_components: int) -> "Pca":
         return cls(n_components)
+
+    @classmethod
+    def from_json(cls, text: str, dtype=np.float64, ctx: Context | None = None) -> "Pca":
+        """`serde_json::from_str::<Pca<A>>` with A = dtype; extra fields (a RandomizedPca's "rng") are ignored."""
+        import json
+        m = cls(0, ctx=ctx)
+        m._load_json_fields(json.loads(text), np.dtype(dtype))
+        return m
 
     def _inner_fit(self, x, want_scores: bool):
         a = _Arr(x)
@@ -434,6 +507,19 @@ class RandomizedPca(_PcaBase):
     @classmethod
     def with_rng(cls, n_components: int, rng: Pcg) -> "RandomizedPca":
         return cls(n_components, rng)
+
+    def _json_fields(self) -> dict:
+        out = {"rng": self.rng.to_json_obj()}  # first field of the struct, src/pca.rs:322
+        out.update(super()._json_fields())
+        return out
+
+    @classmethod
+    def from_json(cls, text: str, dtype=np.float64, ctx: Context | None = None) -> "RandomizedPca":
+        import json
+        obj = json.loads(text)
+        m = cls(0, Pcg.from_json_obj(obj["rng"]), ctx=ctx)
+        m._load_json_fields(obj, np.dtype(dtype))
+        return m
 
     def _inner_fit(self, x, want_scores: bool, omega: np.ndarray | None = None):
         a = _Arr(x)
@@ -578,6 +664,24 @@ class FastIca:
 
     def fit_transform(self, x, w_init=None):
         return self._inner_fit(x, True, w_init)
+
+    def to_json(self) -> str:
+        """serde form of `FastIca { rng, components, means, n_iter }` (src/ica.rs:41-50; test :422-432)."""
+        import json
+        dt = self.components.dtype if self.components.dtype in _SUFFIX else np.dtype(np.float64)
+        return json.dumps({"rng": self.rng.to_json_obj(), "components": _json_array(self.components.astype(dt, copy=False)),
+                           "means": _json_array(np.asarray(self.means, dtype=dt)), "n_iter": int(self.n_iter)},
+                          separators=(",", ":"))
+
+    @classmethod
+    def from_json(cls, text: str, dtype=np.float64, ctx: Context | None = None) -> "FastIca":
+        import json
+        obj = json.loads(text)
+        m = cls(Pcg.from_json_obj(obj["rng"]), ctx=ctx)
+        m.components = _array_from_json(obj["components"], np.dtype(dtype), 2)
+        m.means = _array_from_json(obj["means"], np.dtype(dtype), 1)
+        m.n_iter = int(obj["n_iter"])
+        return m
 
     def transform(self, x):
         a = _Arr(x)

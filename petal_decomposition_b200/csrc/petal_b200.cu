@@ -73,6 +73,85 @@ __global__ void finish_mean_kernel(const double* __restrict__ sum, double inv_n,
     mean_d[j] = (double)mt;  // the mean that is actually subtracted (type A, like the reference)
 }
 
+// ---- column means folded into the range finder's first two passes (randomized PCA, panel path) ----
+// provisional mean mu~ = (T)(sum / count) from a row sample; sum[d] carries the sample's row count
+template <typename T>
+__global__ void provisional_mean_kernel(const double* __restrict__ sum, int64_t d, double* __restrict__ mean_d,
+                                        T* __restrict__ mean_t) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    const double cnt = sum[d];
+    const T mt = (T)(cnt > 0.0 ? sum[j] / cnt : 0.0);
+    mean_t[j] = mt;
+    mean_d[j] = (double)mt;
+}
+// c = column sums of X - mu~ (last column of Zt [d x (l+1)]), delta = (T)(mu~ + c / n) - mu~ (the mean that will be
+// subtracted from now on, minus the provisional one);  wu[0..l) = Omega^T delta, wu[l..2l) = Omega^T c;
+// sc[0] = delta . c, sc[1] = |delta|^2.  One block per Omega column (plus one for the scalars).
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_mean_vectors_kernel(const double* __restrict__ Zt, const T* __restrict__ Omega, int64_t ldo, int64_t d, int64_t l,
+                         double inv_n, const double* __restrict__ mean_d, double* __restrict__ wu, double* __restrict__ sc) {
+    const int64_t col = blockIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int64_t j = threadIdx.x; j < d; j += 256) {
+        const double c = Zt[j * (l + 1) + l];
+        const double delta = (double)(T)(mean_d[j] + c * inv_n) - mean_d[j];
+        if (col < l) {
+            const double om = (double)Omega[j * ldo + col];
+            a += om * delta;
+            b += om * c;
+        } else {
+            a += delta * c;
+            b += delta * delta;
+        }
+    }
+    __shared__ double ra[256], rb[256];
+    ra[threadIdx.x] = a;
+    rb[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int i = 0; i < 256; ++i) {
+            sa += ra[i];
+            sb += rb[i];
+        }
+        if (col < l) {
+            wu[col] = sa;
+            wu[l + col] = sb;
+        } else {
+            sc[0] = sa;
+            sc[1] = sb;
+        }
+    }
+}
+// Z[j][c] = Zt[j][c] - c_j w_c - delta_j u_c + n delta_j w_c   (= (X - mu)^T ((X - mu) Omega) from the products taken
+// with the provisional mean);  mean <- mu~ + delta;  tv <- tv - 2 delta.c + n |delta|^2 (thread 0)
+// (tv is still this rank's partial sum and is all-reduced later: each rank applies its 1/world share of the correction)
+template <typename T>
+__global__ void fold_mean_fix_kernel(const double* __restrict__ Zt, int64_t d, int64_t l, double inv_n, double n_total,
+                                     const double* __restrict__ wu, const double* __restrict__ sc, const double* __restrict__ mean_d,
+                                     double inv_world, double* __restrict__ Z, double* __restrict__ tv) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) *tv = *tv + inv_world * (-2.0 * sc[0] + n_total * sc[1]);
+    if (idx >= d * l) return;
+    const int64_t j = idx / l, c = idx % l;
+    const double cs = Zt[j * (l + 1) + l];
+    const double mu0 = mean_d[j];
+    const T mt = (T)(mu0 + cs * inv_n);
+    const double delta = (double)mt - mu0;
+    Z[idx] = Zt[j * (l + 1) + c] - cs * wu[c] - delta * wu[l + c] + n_total * delta * wu[c];
+}
+template <typename T>
+__global__ void fold_mean_commit_kernel(const double* __restrict__ Zt, int64_t d, int64_t l, double inv_n,
+                                        double* __restrict__ mean_d, T* __restrict__ mean_t) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    const T mt = (T)(mean_d[j] + Zt[j * (l + 1) + l] * inv_n);
+    mean_t[j] = mt;
+    mean_d[j] = (double)mt;
+}
+
 __global__ void trace_kernel(const double* __restrict__ G, int64_t d, double* __restrict__ out) {
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < d; i += blockDim.x) s += G[i * d + i];
@@ -542,8 +621,34 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     DevOut<T> comps(ctx, comps_u, (size_t)(k * d)), mean(ctx, mean_u, (size_t)d), sing(ctx, sing_u, (size_t)k),
         tv(ctx, tv_u, 1), scores(ctx, scores_u, (size_t)(n * k));
 
+    // Column means.  On the panel path (f32, tcgen05) with at least one power iteration and a spare padding column
+    // in the Y panel, the separate pass over X is saved: X Omega runs with a provisional mean mu~ taken from a row
+    // sample, its panel carries a column of ones, so the X^T Y pass that follows also returns the column sums of
+    // X - mu~; the exact mean mu = mu~ + delta and the exact Z = Xc^T (Xc Omega), ||Xc||_F^2 follow by rank-one
+    // corrections of the small side (delta ~ sigma / sqrt(sample): no cancellation).
     ColMean<T> cm;
-    compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
+    bool fold_mean = false;
+    if constexpr (sizeof(T) == 4) {
+        const int64_t l_ = std::min<int64_t>(l_full, std::min<int64_t>(n_total, d));
+        fold_mean = ginfo.cap[0] && centering && n_iter >= 1 && (l_ % 16) != 0;
+        if (const char* e = getenv("PETAL_FOLD_MEAN")) fold_mean = fold_mean && atoi(e) != 0;
+    }
+    if (fold_mean) {
+        cm.mean_d.alloc(ctx, (size_t)d);
+        cm.mean_t.alloc(ctx, (size_t)d);
+        DBuf<double> sum(ctx, (size_t)d + 1);
+        sum.zero();
+        const int64_t rows_s = std::min<int64_t>(n, 8192);
+        launch_colsum<T>(ctx, X.p, rows_s, d, d, sum.p);
+        set_value_kernel<<<1, 1, 0, ctx->stream>>>(sum.p + d, (double)rows_s);
+        launch1(ctx);
+        allreduce_sum(ctx, sum.p, (size_t)d + 1);
+        provisional_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, d, cm.mean_d.p, cm.mean_t.p);
+        launch1(ctx);
+        cm.mu = cm.mean_t.p;
+    } else {
+        compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
+    }
     const double cutoff = rank_cutoff<T>();
     pc.mark("stage inputs + mean");
 
@@ -576,8 +681,9 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         // the power iterations in between only have to keep the dominant subspace and use the faster long chains.
         if (panel)
             tc::launch_tc_xb<float>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, Y.p, ly, tvd, true, Ylo.p,
-                                    n_iter == 0 ? -1 : 0);
+                                    n_iter == 0 ? -1 : 0, nullptr, -1, fold_mean ? (int)l : -1);
     }
+    if (fold_mean && !panel) linalg_error("inconsistent panel-path decision (folded mean)");
     if (!panel) gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
 
     pc.mark("Y = Xc Omega");
@@ -599,8 +705,32 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     int64_t fast_atb_iters = 0;
     if (const char* e = getenv("PETAL_ATB_FAST_ITERS")) fast_atb_iters = atoi(e);
     for (int64_t it = 0; it < n_iter; ++it) {
-        xty_pass(Zd.p, it < fast_atb_iters ? 0 : -1);
-        allreduce_sum(ctx, Zd.p, (size_t)(d * l));
+        bool folded = false;
+        if constexpr (sizeof(T) == 4) {
+            if (fold_mean && it == 0) {
+                // Zt [d x (l + 1)] = (X - mu~)^T [Y~ | 1], then the rank-one corrections
+                DBuf<double> Zt(ctx, (size_t)(d * (l + 1))), wu(ctx, (size_t)(2 * l)), sc(ctx, 2);
+                Zt.zero();
+                tc::launch_tc_atb(ctx, X.p, d, d, cm.mu, Y.p, ly, l + 1, n, Zt.p, l + 1, true, Ylo.p, nullptr,
+                                  it < fast_atb_iters ? 0 : -1);
+                allreduce_sum(ctx, Zt.p, (size_t)(d * (l + 1)));
+                const double inv_n = 1.0 / (double)n_total;
+                fold_mean_vectors_kernel<T><<<(unsigned)(l + 1), 256, 0, ctx->stream>>>(Zt.p, Omega.p, l_full, d, l, inv_n,
+                                                                                       cm.mean_d.p, wu.p, sc.p);
+                launch1(ctx);
+                fold_mean_fix_kernel<T><<<(unsigned)ceil_div(d * l, 256), 256, 0, ctx->stream>>>(
+                    Zt.p, d, l, inv_n, (double)n_total, wu.p, sc.p, cm.mean_d.p, 1.0 / (double)ctx->world, Zd.p, tvd);
+                launch1(ctx);
+                fold_mean_commit_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(Zt.p, d, l, inv_n, cm.mean_d.p,
+                                                                                             cm.mean_t.p);
+                launch1(ctx);
+                folded = true;
+            }
+        }
+        if (!folded) {
+            xty_pass(Zd.p, it < fast_atb_iters ? 0 : -1);
+            allreduce_sum(ctx, Zd.p, (size_t)(d * l));
+        }
         pc.mark("  Z = Xc^T Y");
         orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
         pc.mark("  orth(Z)");

@@ -99,6 +99,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (mbar_try_wait(bar, parity)) return;
     mbar_timeout(bar, parity);
 }
+// Wait with back-off for roles that run ahead of their consumer (TMA producers waiting for a free stage, transform
+// warps waiting for a TMEM operand slot): between probes the thread sleeps ~ns instead of re-issuing try_wait - the
+// hardware's suspended try_wait wakes on every barrier event of the CTA, which made these loops 40 % of tc_atb's
+// warp instructions (r02 ncu source page).  Wake-up is late by at most ~2 ns_ : only for waits with slack.
+#ifndef PETAL_WAIT_BACKOFF
+#define PETAL_WAIT_BACKOFF 1
+#endif
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
+#if PETAL_WAIT_BACKOFF
+    if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+    for (uint32_t it = 0; it < 40000000u; ++it) {
+        __nanosleep(ns);
+        if (mbar_try_wait(bar, parity)) return;
+    }
+    mbar_timeout(bar, parity);
+#else
+    (void)ns;
+    mbar_wait(bar, parity);
+#endif
+}
 // non-blocking probe of a barrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -238,6 +259,8 @@ struct TcParams {
     const float* bias;    // tc_xb, row-major Y: per output column, added in the epilogue (nullable)
     int64_t y_cols;       // tc_xb, row-major Y: columns of a Y row that may be written (the row pitch, or the width of
                           // a column block when Y is a window of a wider matrix)
+    int ones_col_p1;      // tc_xb, panel-major Y: 1 + index of a padding column that is written as 1.0 (valid rows) instead of
+                          // 0 - the X^T Y pass that follows then delivers the column sums of X - mu for free; 0 = none
     // tc_atb outputs / decomposition
     double* Z;            // [da x ldz] f64, atomically accumulated
     int64_t ldz;
@@ -502,7 +525,8 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 if (blk_valid) {
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
-                        const float y = valid ? __uint_as_float(w[jj]) : 0.f;
+                        float y = valid ? __uint_as_float(w[jj]) : 0.f;
+                        if (c0 + jj + 1 == p.ones_col_p1) y = valid ? 1.f : 0.f;
                         yb[(c0 + jj) * 32] = y;
                         if (p.Ylo != nullptr) yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
                     }
@@ -597,7 +621,8 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
             const bool valid = r < p.n;
 #pragma unroll
             for (int jj = 0; jj < 16; ++jj) {
-                const float y = valid ? w[jj] : 0.f;
+                float y = valid ? w[jj] : 0.f;
+                if (c0 + jj + 1 == p.ones_col_p1) y = valid ? 1.f : 0.f;
                 yb[(c0 + jj) * 32] = y;
                 if (p.Ylo != nullptr) yl[(c0 + jj) * 32] = y - __uint_as_float(__float_as_uint(y) & 0xFFFFE000u);
             }
@@ -758,7 +783,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 }
                 // TMEM operand slot `ta` must have been drained by the MMAs of two K blocks ago
                 if (warp == 0 && lane == 0) trace_ev(p, 4, it);
-                mbar_wait(bar_a_free(bars, ta), pa ^ 1u);
+                mbar_wait_relaxed(bar_a_free(bars, ta), pa ^ 1u, 48);
                 tc_fence_after();
                 if (warp == 0 && lane == 0) trace_ev(p, 5, it);
                 const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kASlotCols + mt * 32);
@@ -957,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 if (it >= 1) {
                     const uint32_t nxt = it - 1u + (uint32_t)SB;
                     if (nxt < total && lane == 0) {
-                        mbar_wait(bar_empty_b(bars, rr.s), rr.ph);  // MMAs of block it-1 have read the stage
+                        mbar_wait_relaxed(bar_empty_b(bars, rr.s), rr.ph, 64);  // MMAs of block it-1 have read the stage
                         load_block(nxt, rr.s);
                     }
                     rr.advance();
@@ -974,7 +999,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it, rx.advance()) {
                         const int s = rx.s;
                         const uint32_t ph = rx.ph;
-                        mbar_wait(bar_empty_x(bars, s), ph ^ 1u);
+                        mbar_wait_relaxed(bar_empty_x(bars, s), ph ^ 1u, 128);
                         trace_ev(p, 0, it);
                         const uint32_t full = bar_full(bars, s);
                         if (ATB) {
@@ -1004,7 +1029,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     for (int64_t kb = 0; kb < g.kblocks; ++kb, ++it, rb.advance()) {
                         const int sb = rb.s;
                         const uint32_t phb = rb.ph;
-                        mbar_wait(bar_empty_b(bars, sb), phb ^ 1u);
+                        mbar_wait_relaxed(bar_empty_b(bars, sb), phb ^ 1u, 64);
                         const uint32_t fullb = bar_full_b(bars, sb);
                         if (ATB && panel) {
                             // panel-major Y: rows (r/32)*n_pad .. +n_pad of the [blocks*n_pad][32] views are exactly
@@ -1248,7 +1273,7 @@ template <typename TS>
 void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_t K, const TS* B, int64_t ldb,
                   bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq,
                   bool y_panel = false, float* Y_lo_panel = nullptr, int precise = -1, const float* bias = nullptr,
-                  int64_t y_cols = -1) {
+                  int64_t y_cols = -1, int ones_col = -1) {
     const int n_pad = round_up(L, 16);
     int stages = 0, stages_b = 0;
     if (!pick_stages(false, n_pad, false, stages, stages_b)) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
@@ -1278,6 +1303,7 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     p.L = (int)L;
     p.y_vec = (is_aligned16(Y) && (ldy % 4 == 0) && (p.y_cols % 2 == 0)) ? 1 : 0;
     p.y_panel = y_panel ? 1 : 0;
+    p.ones_col_p1 = (y_panel && ones_col >= 0 && ones_col < n_pad) ? ones_col + 1 : 0;
     p.Ylo = Y_lo_panel;
     p.sumsq = sumsq;
     // mode (see ModeTraits): two accumulator sets need 192 + 4 n_pad <= 512

@@ -562,3 +562,35 @@ def test_dmma_gram_engines(pd, n, d):
         z = pd.xty(x, y, mean)
         assert np.allclose(z, (x - mean).T @ y, rtol=1e-12, atol=1e-11 * n)
     ctx.set_f64_engine(1)
+
+
+# ------------------------------------------------------------ serde (reference tests with feature "serde")
+def test_ref_pca_serialize(pd):  # src/pca.rs:935-947
+    pca = pd.Pca.new(1)
+    x = np.array([[1.0, 1.0]], dtype=np.float32)
+    pca.fit(x)
+    back = pd.Pca.from_json(pca.to_json(), np.float32)
+    assert np.allclose(back.components(), pca.components(), atol=1e-12)
+    assert np.allclose(back.mean(), pca.mean())
+    assert np.allclose(back.transform(x), pca.transform(x))
+
+
+def test_ref_randomized_pca_serialize(pd):  # src/pca.rs:1029-1041 (read back as a Pca, like the reference does)
+    pca = pd.RandomizedPca.with_seed(1, RNG_SEED)
+    x = np.array([[1.0, 1.0]], dtype=np.float32)
+    pca.fit(x)
+    back = pd.Pca.from_json(pca.to_json(), np.float32)
+    assert np.allclose(back.components(), pca.components(), atol=1e-12)
+    assert np.allclose(back.mean(), pca.mean())
+    again = pd.RandomizedPca.from_json(pca.to_json(), np.float32)
+    assert again.rng.state() == pca.rng.state()
+
+
+def test_ref_fast_ica_serialize(pd):  # src/ica.rs:422-432
+    x = np.array([[0.0, 0.0], [1.0, 1.0], [1.0, -1.0]])
+    ica = pd.FastIca.new()
+    ica.fit(x)
+    back = pd.FastIca.from_json(ica.to_json())
+    assert np.allclose(back.components, ica.components, atol=1e-12)
+    assert np.allclose(back.means, ica.means)
+    assert np.allclose(back.transform(x), ica.transform(x))

@@ -132,3 +132,44 @@ def test_cpp_host_mirror_compiles(lib, tmp_path):
         assert out.split()[:3] == ["5", "0", "5"] or abs(float(out.split()[0]) - 5) < 1e-9
     else:
         assert "linear algerba operation failed" in out and "no CPU fallback" in out
+
+
+# ------------------------------------------------------------------ serde wire format (host logic, no GPU)
+def test_serde_wire_format_round_trip(lib):
+    """Field names / order of the reference structs (src/pca.rs:41-51,317-329; src/ica.rs:41-50), ndarray's
+    {"v","dim","data"} arrays, rand_pcg's {"state": u128}."""
+    import json
+    import petal_decomposition_b200 as pd
+    m = pd.Pca.new(1)
+    m._components = np.array([[0.70710677, 0.70710677]], dtype=np.float32)
+    m._means = np.array([1, 1], np.float32)
+    m._singular = np.array([0.0], np.float32)
+    m._total_variance, m._n_samples = 0.0, 1
+    text = m.to_json()
+    assert text == ('{"components":{"v":1,"dim":[1,2],"data":[0.70710677,0.70710677]},"n_samples":1,'
+                    '"means":{"v":1,"dim":[2],"data":[1.0,1.0]},"total_variance":0.0,'
+                    '"singular":{"v":1,"dim":[1],"data":[0.0]},"centering":true}')
+    back = pd.Pca.from_json(text, np.float32)
+    assert back.components().dtype == np.float32 and np.array_equal(back.components(), m.components())
+    assert np.array_equal(back.mean(), m.mean()) and back.n_components() == 1
+
+    r = pd.RandomizedPca.with_seed(1, 1_234_567_891_011_121_314)
+    r._components, r._means, r._singular = m._components, m._means, m._singular
+    doc = json.loads(r.to_json())
+    assert list(doc) == ["rng", "components", "n_samples", "means", "total_variance", "singular", "centering"]
+    assert doc["rng"] == {"state": r.rng.state()} and doc["rng"]["state"] % 2 == 1
+    r2 = pd.RandomizedPca.from_json(r.to_json(), np.float32)
+    assert r2.rng.state() == r.rng.state() and r2.rng.next_u64() == r.rng.next_u64()
+    # the reference's randomized_pca_serialize test reads the RandomizedPca document into a Pca (src/pca.rs:1037)
+    assert np.array_equal(pd.Pca.from_json(r.to_json(), np.float32).components(), m.components())
+
+    ica = pd.FastIca.with_seed(7)
+    ica.components = np.array([[1.5, -2.0], [0.25, 4.0]])
+    ica.means = np.array([0.5, -0.5])
+    ica.n_iter = 3
+    doc = json.loads(ica.to_json())
+    assert list(doc) == ["rng", "components", "means", "n_iter"] and doc["n_iter"] == 3
+    i2 = pd.FastIca.from_json(ica.to_json())
+    assert np.array_equal(i2.components, ica.components) and np.array_equal(i2.means, ica.means) and i2.n_iter == 3
+    with pytest.raises(pd.InvalidInput):
+        pd.Pca.from_json(text.replace('"dim":[1,2]', '"dim":[3,2]'), np.float32)
