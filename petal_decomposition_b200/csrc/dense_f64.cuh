@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) gemm_nn_dmma_kernel(GemmParams p) {
         for (int j = 0; j < 8; ++j) {
             const int64_t k = k0 + ak + j;
             double v = 0.0;
-            if (r < p.M && k < k_end) v = p.A[r * p.lda + k] - (p.mu ? p.mu[k] : 0.0);
+            if (r < p.M && k < k_end) v = p.A[r * p.lda + k];  // centred when stored (keeps the prefetch asynchronous)
             a_st[j] = v;
         }
         const int64_t k = k0 + bk;
@@ -82,15 +82,19 @@ __global__ void __launch_bounds__(256) gemm_nn_dmma_kernel(GemmParams p) {
             b_st[j] = v;
         }
     };
-    auto store_chunk = [&]() {
+    auto store_chunk = [&](int64_t k0) {
+        const bool row_ok = (r0 + ar) < p.M;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) As[ar * LDA + ak + j] = a_st[j];
+        for (int j = 0; j < 8; ++j) {
+            const int64_t k = k0 + ak + j;
+            As[ar * LDA + ak + j] = (p.mu && row_ok && k < k_end) ? a_st[j] - p.mu[k] : a_st[j];
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) Bs[bk * LDB + bc + j] = b_st[j];
     };
     if (k_begin < k_end) {
         load_chunk(k_begin);
-        store_chunk();
+        store_chunk(k_begin);
     }
     __syncthreads();
     for (int64_t k0 = k_begin; k0 < k_end; k0 += KC) {
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(256) gemm_nn_dmma_kernel(GemmParams p) {
         }
         __syncthreads();
         if (has_next) {
-            store_chunk();
+            store_chunk(k0 + KC);
             __syncthreads();
         }
     }
@@ -442,55 +446,91 @@ bj_update_kernel(double* __restrict__ M, int64_t len, int nblk, int step, const 
     }
 }
 
-// Batched 64 x 64 two-sided Jacobi on G_p = A_p A_p^T: the orthogonal J_p with J_p G_p J_p^T diagonal.
-// A rotation of rows (p, q) of A_p depends only on G_pp, G_qq, G_pq, so this is the scalar one-sided Jacobi on the 64
-// rows of A_p carried out on their Gram matrix (G <- J G J^T) instead of on the rows themselves; the rows are
-// rotated once, afterwards, by one GEMM with the accumulated J_p.  The rotation test is the scale-invariant
-// |G_pq| > tol sqrt(G_pp G_qq) of one-sided Jacobi - the computed Gram entries are accurate relative to
-// sqrt(G_pp G_qq), so rows of very different norms are resolved (an eigen-solver with an absolute noise floor
-// eps * lambda_max, as first tried, stalls at cos ~ eps * sigma_max / sigma_min).
-// One CTA per pair, 512 threads = 32 groups of 16 lanes (one per row pair of a round-robin step); G and J live in
-// shared memory with a row pitch of 65 (the column phase walks a column: conflict-free).
-constexpr int kBJEigThreads = 512;
-constexpr int kBJEigLD = kBJ2 + 1;
-__global__ void __launch_bounds__(kBJEigThreads)
-bj_eig_kernel(const double* __restrict__ Gp, double* __restrict__ Jp, const int* __restrict__ active, int max_sweeps,
-              double tol, double zero_floor2, const double* __restrict__ amax2) {
-    if (!active[blockIdx.x]) return;
-    constexpr int m = kBJ2, LD = kBJEigLD;
+// Two-sided Jacobi on a small symmetric positive semi-definite matrix in shared memory (m <= kSymMaxM), batched over
+// blockIdx.x: the orthogonal J with J G J^T diagonal.
+//  * block Jacobi: G_p = A_p A_p^T of a pair of row blocks.  A rotation of rows (p, q) of A_p depends only on G_pp,
+//    G_qq, G_pq, so this is the scalar one-sided Jacobi on the 64 rows of A_p carried out on their Gram matrix
+//    (G <- J G J^T) instead of on the rows themselves; the rows are rotated once, afterwards, by one GEMM with J_p.
+//  * stand-alone (sort = 1): rows of J are the eigenvectors, the diagonal the eigenvalues, sorted descending.
+//    (Tried in r02 as the eigensolver of the small Gram matrices - whitening, the range finder's l x l blocks - it
+//    was no faster than the one-sided engine on the same matrices: both are bound by barriers per round-robin step.)
+// The rotation test is the scale-invariant |G_pq| > tol sqrt(G_pp G_qq) of one-sided Jacobi: computed Gram entries
+// are accurate relative to sqrt(G_pp G_qq), so rows of very different norms are resolved (an eigen-solver with an
+// absolute noise floor eps * lambda_max, as first tried, stalls at cos ~ eps * sigma_max / sigma_min).
+// 512 threads = 32 groups of 16 lanes, one group per pair of a round-robin step: rotation parameters, rows of G and J,
+// then columns of G (three barriers per step).
+// Row pitch me + 1 (odd): the column phase walks a column without bank conflicts.
+constexpr int kSymMaxM = 112;
+constexpr int kSymThreads = 512;
+inline size_t sym_jacobi_smem(int m) {
+    const int me = (m + 1) & ~1;
+    return (size_t)(2 * me * (me + 1) + 2 * (me / 2) + me) * sizeof(double);
+}
+__global__ void __launch_bounds__(kSymThreads)
+jacobi_sym_kernel(const double* __restrict__ Gin, int64_t g_stride, int m, double* __restrict__ Jout, int64_t j_stride,
+                  double* __restrict__ lam_out /* nullable: sorted eigenvalues */, const int* __restrict__ active /* nullable */,
+                  const int* __restrict__ run_flag /* nullable */, int max_sweeps, double tol, double floor_rel,
+                  const double* __restrict__ amax2 /* nullable: floor^2 = floor_rel^2 * amax2, else floor = floor_rel * max diag */,
+                  int sort, int* __restrict__ status) {
+    if (active != nullptr && !active[blockIdx.x]) return;
+    if (run_flag != nullptr && *run_flag == 0) return;
+    const int me = (m + 1) & ~1, LD = me + 1, np = me / 2;
     extern __shared__ double esm[];
     double* Gs = esm;
-    double* Js = esm + m * LD;
+    double* Js = esm + me * LD;
+    double* rc = esm + 2 * me * LD;   // [np] cos
+    double* rs = rc + np;             // [np] sin (0: no rotation)
+    double* dg = rs + np;             // [me] scratch (max diag / sort)
     __shared__ int rotated;
-    const double* A = Gp + (size_t)blockIdx.x * m * m;
+    const double* A = Gin + (size_t)blockIdx.x * g_stride;
     const int tid = threadIdx.x;
-    for (int i = tid; i < m * m; i += kBJEigThreads) {
-        const int r = i / m, c = i % m;
-        // symmetrise on load: the two halves of the Gram differ by the rounding of differently ordered sums
-        Gs[r * LD + c] = (c >= r) ? A[i] : A[c * m + r];
+    for (int i = tid; i < me * me; i += kSymThreads) {
+        const int r = i / me, c = i % me;
+        double v = 0.0;
+        if (r < m && c < m) v = (c >= r) ? A[(size_t)r * m + c] : A[(size_t)c * m + r];  // symmetrised on load
+        Gs[r * LD + c] = v;
         Js[r * LD + c] = (r == c) ? 1.0 : 0.0;
     }
     if (tid == 0) rotated = 0;
     __syncthreads();
-    const double floor2 = zero_floor2 * (*amax2);
+    double floor_abs;
+    if (amax2 != nullptr) {
+        floor_abs = floor_rel * floor_rel * (*amax2);
+    } else {
+        double md = 0.0;
+        for (int i = 0; i < m; ++i) md = fmax(md, Gs[i * LD + i]);
+        floor_abs = floor_rel * md;
+    }
     const int gid = tid >> 4, gl = tid & 15;
-    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-        for (int step = 0; step < m - 1; ++step) {
-            int p, q;
-            rr_pair(m, step, gid, p, q);
-            const double al = Gs[p * LD + p], be = Gs[q * LD + q], ga = Gs[p * LD + q];
-            double c = 1.0, sn = 0.0;
-            bool rot = false;
-            if (al > floor2 && be > floor2 && fabs(ga) > tol * sqrt(al * be)) {
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                c = rsqrt(1.0 + t * t);
-                sn = c * t;
-                rot = true;
+    bool converged = (m <= 1);
+    for (int sweep = 0; sweep < max_sweeps && m > 1; ++sweep) {
+        for (int step = 0; step < me - 1; ++step) {
+            // every 16-lane group owns pairs gid, gid + 32, ... of the step and computes their rotations itself
+            double cc[(kSymMaxM / 2 + 31) / 32], ss[(kSymMaxM / 2 + 31) / 32];
+#pragma unroll
+            for (int u = 0; u < (kSymMaxM / 2 + 31) / 32; ++u) {
+                const int pi = gid + u * (kSymThreads / 16);
+                cc[u] = 1.0;
+                ss[u] = 0.0;
+                if (pi < np) {
+                    int p, q;
+                    rr_pair(me, step, pi, p, q);
+                    if (q < m) {
+                        const double al = Gs[p * LD + p], be = Gs[q * LD + q], ga = Gs[p * LD + q];
+                        if (al > floor_abs && be > floor_abs && fabs(ga) > tol * sqrt(al * be))
+                            rotation_from(al, be, ga, cc[u], ss[u], nullptr);
+                    }
+                }
             }
             __syncthreads();  // every group has read its (al, be, ga) before rows change
-            if (rot) {
-                for (int e = gl; e < m; e += 16) {  // rows p, q of G and of J
+#pragma unroll
+            for (int u = 0; u < (kSymMaxM / 2 + 31) / 32; ++u) {
+                const int pi = gid + u * (kSymThreads / 16);
+                if (pi >= np || ss[u] == 0.0) continue;
+                int p, q;
+                rr_pair(me, step, pi, p, q);
+                const double c = cc[u], sn = ss[u];
+                for (int e = gl; e < me; e += 16) {  // rows p, q of G and of J
                     const double x = Gs[p * LD + e], y = Gs[q * LD + e];
                     Gs[p * LD + e] = c * x - sn * y;
                     Gs[q * LD + e] = sn * x + c * y;
@@ -501,32 +541,63 @@ bj_eig_kernel(const double* __restrict__ Gp, double* __restrict__ Jp, const int*
                 if (gl == 0) rotated = 1;
             }
             __syncthreads();
-            if (rot) {
-                for (int e = gl; e < m; e += 16) {  // columns p, q of G
+#pragma unroll
+            for (int u = 0; u < (kSymMaxM / 2 + 31) / 32; ++u) {
+                const int pi = gid + u * (kSymThreads / 16);
+                if (pi >= np || ss[u] == 0.0) continue;
+                int p, q;
+                rr_pair(me, step, pi, p, q);
+                const double c = cc[u], sn = ss[u];
+                for (int e = gl; e < me; e += 16) {  // columns p, q of G
+                    if (e == p || e == q) continue;   // the 2 x 2 block is set below
                     const double x = Gs[e * LD + p], y = Gs[e * LD + q];
                     Gs[e * LD + p] = c * x - sn * y;
                     Gs[e * LD + q] = sn * x + c * y;
                 }
+                if (gl == 0) {
+                    // 2 x 2 block after the row phase: [[g_pp', g_pq'], [g_qp', g_qq']] times R^T
+                    const double a = Gs[p * LD + p], b = Gs[p * LD + q], d2 = Gs[q * LD + p], e2 = Gs[q * LD + q];
+                    Gs[p * LD + p] = c * a - sn * b;
+                    Gs[q * LD + q] = sn * d2 + c * e2;
+                    Gs[p * LD + q] = 0.0;  // annihilated (exactly, up to the approximation of the angle: next sweep)
+                    Gs[q * LD + p] = 0.0;
+                }
             }
             __syncthreads();
-            if (rot && gl == 0) {
-                Gs[p * LD + q] = 0.0;  // annihilated exactly
-                Gs[q * LD + p] = 0.0;
-            }
         }
-        __syncthreads();
         const int r = rotated;
         __syncthreads();
         if (tid == 0) rotated = 0;
         __syncthreads();
-        if (!r) break;
+        if (!r) {
+            converged = true;
+            break;
+        }
     }
-    // (an inner solve that ran out of sweeps still hands back an exactly orthogonal J: the outer iteration continues)
-    double* out = Jp + (size_t)blockIdx.x * m * m;
-    for (int i = tid; i < m * m; i += kBJEigThreads) out[i] = Js[(i / m) * LD + (i % m)];
+    if (!converged && status != nullptr && tid == 0) atomicOr(status, kStatusJacobiNotConverged);
+    double* out = Jout + (size_t)blockIdx.x * j_stride;
+    if (!sort) {
+        for (int i = tid; i < m * m; i += kSymThreads) out[i] = Js[(i / m) * LD + (i % m)];
+        return;
+    }
+    for (int j = tid; j < m; j += kSymThreads) dg[j] = Gs[j * LD + j];
+    __syncthreads();
+    for (int j = tid >> 5; j < m; j += kSymThreads / 32) {  // one warp per row: rank = position in descending order
+        const int lane = tid & 31;
+        const double sj = dg[j];
+        int rank = 0;
+        for (int i = lane; i < m; i += 32) {
+            const double si = dg[i];
+            rank += (si > sj || (si == sj && i < j)) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+        if (lane == 0 && lam_out != nullptr) lam_out[(size_t)blockIdx.x * m + rank] = fmax(sj, 0.0);
+        for (int e = lane; e < m; e += 32) out[(size_t)rank * m + e] = Js[j * LD + e];
+    }
 }
 
-constexpr size_t kBJEigSmem = (size_t)(2 * kBJ2 * kBJEigLD) * sizeof(double);
+
 
 __global__ void bj_amax2_kernel(const double* __restrict__ nrm, int m, double* __restrict__ amax2) {
     double a = 0.0;
@@ -559,7 +630,7 @@ inline void block_jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_
     DBuf<int> active(ctx, (size_t)npairs);
     DBuf<unsigned long long> sweep_off(ctx, 1);
     ensure_dynamic_smem(ctx, bj_update_kernel, kBJUpdSmem);
-    ensure_dynamic_smem(ctx, bj_eig_kernel, kBJEigSmem);
+    ensure_dynamic_smem(ctx, jacobi_sym_kernel, sym_jacobi_smem(kSymMaxM));
     int max_sweeps = 40;
     if (const char* e = getenv("PETAL_JACOBI_MAX_SWEEPS")) max_sweeps = std::max(1, atoi(e));
     const double tol = 8.0 * 2.220446049250313e-16 * std::sqrt((double)std::max<int64_t>(len, 1));
@@ -581,8 +652,8 @@ inline void block_jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_
             check_launch(ctx);
             bj_offdiag_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(Gp.p, tol, zero2, amax2.p, active.p, sweep_off.p);
             check_launch(ctx);
-            bj_eig_kernel<<<(unsigned)npairs, kBJEigThreads, kBJEigSmem, ctx->stream>>>(Gp.p, Jp.p, active.p, 30, inner_tol, zero2,
-                                                                                         amax2.p);
+            jacobi_sym_kernel<<<(unsigned)npairs, kSymThreads, sym_jacobi_smem(kBJ2), ctx->stream>>>(
+                Gp.p, kBJ2 * kBJ2, kBJ2, Jp.p, kBJ2 * kBJ2, nullptr, active.p, nullptr, 30, inner_tol, zfloor, amax2.p, 0, nullptr);
             check_launch(ctx);
             bj_update_kernel<<<dim3((unsigned)npairs, ucols), 256, kBJUpdSmem, ctx->stream>>>(M.p, len, nblk, step, Jp.p, active.p);
             check_launch(ctx);

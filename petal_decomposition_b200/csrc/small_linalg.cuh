@@ -43,6 +43,19 @@ __device__ __forceinline__ void rr_pair(int me, int s, int i, int& p, int& q) {
     }
 }
 
+// Rotation (c, s) that annihilates gamma between two rows of squared norms alpha, beta (exact IEEE f64 math:
+// an approximate tangent - MUFU reciprocal / rsqrt + Newton-refined cosine - was tried in r02 and lost: every
+// rotation then leaves a ~1e-6 residual, which costs the inner solves two extra sweeps, more than the cheaper
+// parameter computation saves; the steps of the shared-memory engines are bound by barriers and dependent
+// shared-memory accesses, not by this arithmetic).
+__device__ __forceinline__ void rotation_from(double alpha, double beta, double gamma, double& c, double& s, double* t_out) {
+    const double zeta = (beta - alpha) / (2.0 * gamma);
+    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    c = rsqrt(1.0 + t * t);
+    s = c * t;
+    if (t_out) *t_out = t;
+}
+
 // Computes the rotation for a row pair; returns false when already orthogonal to tolerance.
 // `noise` = (relative entry noise of the input) * (largest row norm): rows of a Gram matrix carry
 // absolute noise eps * lambda_max from the start, so two small rows cannot be made orthogonal
@@ -51,16 +64,7 @@ __device__ __forceinline__ bool jacobi_rotation(double alpha, double beta, doubl
                                                 double& c, double& s, double* t_out = nullptr) {
     const double na = sqrt(alpha), nb = sqrt(beta);
     if (!(fabs(gamma) > tol * na * nb + noise * (na + nb))) return false;  // also false for NaN/zero rows
-    // (tried in r01, no change in step time: an all-fp32 tangent with a Newton-refined f64 normalisation, and keeping the
-    // two rows in registers between the inner product and the rotation.  ncu on the 64 x 64 case: issue-bound at
-    // ~6200 warp instructions per round-robin step, 0.5 IPC per scheduler - the f64 pipe's quarter-rate issue, not a
-    // particular latency chain or shared-memory bandwidth.  A block-Jacobi / fp32-sweeps + f64-polish engine is the
-    // way forward.)
-    const double zeta = (beta - alpha) / (2.0 * gamma);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    c = rsqrt(1.0 + t * t);
-    s = c * t;
-    if (t_out) *t_out = t;
+    rotation_from(alpha, beta, gamma, c, s, t_out);
     return true;
 }
 
@@ -465,7 +469,7 @@ inline int jacobi_rows(petal_ctx* ctx, const double* A, int64_t m, int64_t len, 
     KTimer kt(ctx, use_smem ? "jacobi_smem" : "jacobi_global", 0.0);
     ctx->status_armed = true;
     if (use_smem) {
-        ensure_dynamic_smem(ctx, jacobi_smem_kernel, 200 * 1024);
+        ensure_dynamic_smem(ctx, jacobi_smem_kernel, 208 * 1024);
         DBuf<int> info;
         const bool want_info = getenv("PETAL_JACOBI_INFO") != nullptr;
         if (want_info) {

@@ -528,9 +528,24 @@ __global__ void __launch_bounds__(256) atb_dmma_kernel(AtbParams<double> p) {
 #pragma unroll
         for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
+    // The global loads of the next row chunk are issued before the MMA loop and consumed after it: nothing may
+    // touch the staged registers in between (an earlier version subtracted the column means right after the load,
+    // which made every warp wait for HBM before its DMMAs: 32 % of the stall samples, r02 ncu).  The means are
+    // subtracted when the chunk goes to shared memory; a thread's columns do not change, so its means live in
+    // registers.
     Pack<double> a_stage[A_VECS], b_stage[A_VECS];
-    auto load_one = [&](const double* M, int64_t ld, int64_t ncol, const double* mu, int64_t c0, int64_t r0,
-                        Pack<double>* stage) {
+    Pack<double> a_mu[A_VECS], b_mu[A_VECS];
+#pragma unroll
+    for (int q = 0; q < A_VECS; ++q) {
+        const int cv = (tid + q * 256) % (BI / 2);
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int64_t ca = i0 + cv * 2 + v, cb = j0 + cv * 2 + v;
+            a_mu[q].v[v] = (p.mua && ca < p.da) ? p.mua[ca] : 0.0;
+            b_mu[q].v[v] = (p.mub && cb < p.db) ? p.mub[cb] : 0.0;
+        }
+    }
+    auto load_one = [&](const double* M, int64_t ld, int64_t ncol, int64_t c0, int64_t r0, Pack<double>* stage) {
 #pragma unroll
         for (int q = 0; q < A_VECS; ++q) {
             int idx = tid + q * 256;
@@ -541,35 +556,42 @@ __global__ void __launch_bounds__(256) atb_dmma_kernel(AtbParams<double> p) {
             if (r < r_end && c < ncol) {
                 if constexpr (ALIGNED) {
                     z = *reinterpret_cast<const Pack<double>*>(M + r * ld + c);
-                    if (mu) {
-                        z.v[0] -= mu[c];
-                        z.v[1] -= mu[c + 1];
-                    }
                 } else {
 #pragma unroll
                     for (int v = 0; v < 2; ++v)
-                        if (c + v < ncol) z.v[v] = M[r * ld + c + v] - (mu ? mu[c + v] : 0.0);
+                        if (c + v < ncol) z.v[v] = M[r * ld + c + v];
                 }
             }
             stage[q] = z;
         }
     };
     auto load_tiles = [&](int64_t r0) {
-        load_one(p.A, p.lda, p.da, p.mua, i0, r0, a_stage);
-        if (!same) load_one(p.B, p.ldb, p.db, p.mub, j0, r0, b_stage);
+        load_one(p.A, p.lda, p.da, i0, r0, a_stage);
+        if (!same) load_one(p.B, p.ldb, p.db, j0, r0, b_stage);
     };
-    auto store_tiles = [&]() {
+    auto store_tiles = [&](int64_t r0) {
 #pragma unroll
         for (int q = 0; q < A_VECS; ++q) {
             int idx = tid + q * 256;
             int rr = idx / (BI / 2), cv = idx % (BI / 2);
-            *reinterpret_cast<Pack<double>*>(&As[rr * LDS_ + cv * 2]) = a_stage[q];
-            if (!same) *reinterpret_cast<Pack<double>*>(&Bs[rr * LDS_ + cv * 2]) = b_stage[q];
+            const bool row_ok = (r0 + rr) < r_end;  // rows past the slice stay exactly zero
+            Pack<double> a = a_stage[q];
+#pragma unroll
+            for (int v = 0; v < 2; ++v)
+                if (row_ok && i0 + cv * 2 + v < p.da) a.v[v] -= a_mu[q].v[v];
+            *reinterpret_cast<Pack<double>*>(&As[rr * LDS_ + cv * 2]) = a;
+            if (!same) {
+                Pack<double> b = b_stage[q];
+#pragma unroll
+                for (int v = 0; v < 2; ++v)
+                    if (row_ok && j0 + cv * 2 + v < p.db) b.v[v] -= b_mu[q].v[v];
+                *reinterpret_cast<Pack<double>*>(&Bs[rr * LDS_ + cv * 2]) = b;
+            }
         }
     };
 
     load_tiles(r_begin);
-    store_tiles();
+    store_tiles(r_begin);
     __syncthreads();
     const double* Bt = same ? As : Bs;
     const int kq = lane & 3, rq = lane >> 2;
@@ -590,7 +612,7 @@ __global__ void __launch_bounds__(256) atb_dmma_kernel(AtbParams<double> p) {
         }
         __syncthreads();
         if (has_next) {
-            store_tiles();
+            store_tiles(r0 + BR);
             __syncthreads();
         }
     }
@@ -695,7 +717,7 @@ __global__ void __launch_bounds__(256) xb_dmma_kernel(XbParams<double> p) {
         for (int j = 0; j < 8; ++j) {
             const int64_t k = k0 + ak + j;
             double v = 0.0;
-            if (r < p.n && k < p.K) v = p.A[r * p.lda + k] - (p.mu ? p.mu[k] : 0.0);
+            if (r < p.n && k < p.K) v = p.A[r * p.lda + k];  // centred when stored (keeps the prefetch asynchronous)
             a_st[j] = v;
         }
         const int64_t k = k0 + bk;
@@ -707,17 +729,20 @@ __global__ void __launch_bounds__(256) xb_dmma_kernel(XbParams<double> p) {
             b_st[j] = v;
         }
     };
-    auto store_chunk = [&]() {
+    auto store_chunk = [&](int64_t k0) {
+        const bool row_ok = (r0 + ar) < p.n;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            As[ar * LDA + ak + j] = a_st[j];
-            ss += a_st[j] * a_st[j];
+            const int64_t k = k0 + ak + j;
+            const double v = (p.mu && row_ok && k < p.K) ? a_st[j] - p.mu[k] : a_st[j];
+            As[ar * LDA + ak + j] = v;
+            ss += v * v;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) Bs[bk * LDB + bc + j] = b_st[j];
     };
     load_chunk(0);
-    store_chunk();
+    store_chunk(0);
     __syncthreads();
     for (int64_t k0 = 0; k0 < p.K; k0 += KC) {
         const bool has_next = (k0 + KC) < p.K;
@@ -736,7 +761,7 @@ __global__ void __launch_bounds__(256) xb_dmma_kernel(XbParams<double> p) {
         }
         __syncthreads();
         if (has_next) {
-            store_chunk();
+            store_chunk(k0 + KC);
             __syncthreads();
         }
     }

@@ -38,7 +38,7 @@ constexpr int kKB = 32;           // K block: 32 fp32 = 128 B
 constexpr int kXStageBytes = kMT * 128 * kKB * 4;  // 32 KB
 constexpr int kTmemCols = 512;
 constexpr int kYBufs = 3;         // tc_atb, row-major Y: ring of transposed Y tiles (decoupled from the TMEM operand slots)
-constexpr int kASlotsMax = 4;              // TMEM operand ring: one slot per half K block (16 k-values); 3 or 4 slots
+constexpr int kASlotsMax = 5;              // TMEM operand ring: one slot per half K block (16 k-values); 3, 4 or 5 slots
 constexpr int kASlotCols = kMT * 32;       // per slot: MT x (16 hi + 16 lo) columns
 // accumulators start after the operand ring: 4 slots -> column 256, one accumulator set (MT x n_pad columns);
 // 3 slots -> column 192, two sets (tc_xb with n_pad <= 80): the next super-tile's MMAs run while the previous
@@ -104,7 +104,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // hardware's suspended try_wait wakes on every barrier event of the CTA, which made these loops 40 % of tc_atb's
 // warp instructions (r02 ncu source page).  Wake-up is late by at most ~2 ns_ : only for waits with slack.
 #ifndef PETAL_WAIT_BACKOFF
-#define PETAL_WAIT_BACKOFF 1
+#define PETAL_WAIT_BACKOFF 0
 #endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t ns) {
 #if PETAL_WAIT_BACKOFF
@@ -175,6 +175,38 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::f16 (bf16 operands, K = 16 per instruction, fp32 accumulate)
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// two fp32 -> one 32-bit word of two bf16 (round to nearest): `lo` in bits 0-15 (the lower K index), `hi` in 16-31
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+// 2-MMA split ("cross" mode).  x y = xh yh + (xl yh + xh yl) + xl yl with xh = tf32(x), xl = x - xh.  The leading term
+// needs tf32 operands; the two cross terms are 2^-11 of it, so their factors only need ~8 significant bits: they are
+// fed as bf16 and, concatenated along K, cost ONE kind::f16 MMA with K = 16 ([xl | xh] . [yh ; yl] over 8 k values)
+// instead of two kind::tf32 MMAs with K = 8.  Tensor work per K step: 2 MMA slots instead of 3; the error of the
+// bf16 rounding enters at 2^-11 * 2^-9 = 2^-20 relative to the product, unbiased (round to nearest).
+#ifndef PETAL_TC_CROSS
+#define PETAL_TC_CROSS 1
+#endif
+constexpr bool kCrossEnabled = PETAL_TC_CROSS != 0;
+// Used by tc_xb (X B pass: 11.3 -> 9.0 ms at c2, same accuracy in every parity test).  tc_atb keeps the 3 x tf32 form:
+// its B-side cross tile would have to be derived from the fp32 Y panel by the splitter warp (per 8 values 2 LDS +
+// 16 ALU + 8 CVT + 2 STS), and one warp sharing its scheduler with four transform warps cannot do that within a
+// K block - measured (r02): X^T Y pass 10.7 -> 13.1 ms with one splitter warp, 18.9 ms with the X-producer warp as a
+// second splitter (its TMA issue then trails).
+
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -228,6 +260,10 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
 __host__ __device__ inline uint32_t make_idesc_tf32(int n, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(b_mn_major ? 1 : 0) << 16) | ((uint32_t)(n >> 3) << 17) |
            ((uint32_t)(128 >> 4) << 24);
+}
+// instruction descriptor kind::f16 with bf16 A / B (format 1), fp32 accumulate, M = 128, N = n, both K-major
+__host__ __device__ inline uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -318,8 +354,8 @@ __device__ __forceinline__ uint32_t bar_full(uint32_t base, int s) { return base
 __device__ __forceinline__ uint32_t bar_empty_x(uint32_t base, int s) { return base + 8u * (8 + (uint32_t)s); }
 __device__ __forceinline__ uint32_t bar_full_b(uint32_t base, int s) { return base + 8u * (16 + (uint32_t)s); }   // B ring
 __device__ __forceinline__ uint32_t bar_empty_b(uint32_t base, int s) { return base + 8u * (24 + (uint32_t)s); }
-__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (32 + (uint32_t)t); }  // 4 slots
-__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (36 + (uint32_t)t); }
+__device__ __forceinline__ uint32_t bar_a_ready(uint32_t base, int t) { return base + 8u * (t < 4 ? 32u + (uint32_t)t : 56u); }  // 5 slots
+__device__ __forceinline__ uint32_t bar_a_free(uint32_t base, int t) { return base + 8u * (t < 4 ? 36u + (uint32_t)t : 57u); }
 __device__ __forceinline__ uint32_t bar_acc_full(uint32_t base, int b) { return base + 8u * (40 + (uint32_t)b); }   // 40 .. 42
 __device__ __forceinline__ uint32_t bar_acc_empty(uint32_t base, int b) { return base + 8u * (47 + (uint32_t)b); }  // 47 .. 49
 __device__ __forceinline__ uint32_t bar_y_free(uint32_t base, int t) { return base + 8u * (44 + (uint32_t)t); }
@@ -411,9 +447,13 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 template <bool ATB, int MODE>
 struct ModeTraits {
     static constexpr bool kCut = (MODE == 2);
-    static constexpr int kSlots = (!ATB && MODE != 0) ? 3 : 4;
+    // MODE 3 (tc_xb, n_pad <= 96): the fast mode with a 5-slot operand ring (2.5 K blocks between the transform warps
+    // and the MMA issuers instead of 2): both sides spend about half of their time waiting for each other (r02 ncu
+    // source page: 37 % of all warp samples of tc_xb are transform warps waiting for a free operand slot while the
+    // tensor pipe is 57 % busy), so the deeper ring buys overlap
+    static constexpr int kSlots = (!ATB && MODE == 3) ? 5 : ((!ATB && MODE != 0) ? 3 : 4);
     static constexpr int kAccBase = kSlots * kASlotCols;
-    static constexpr int kAccBufs = ATB ? (MODE == 2 ? 3 : 1) : (MODE == 0 ? 1 : 2);
+    static constexpr int kAccBufs = ATB ? (MODE == 2 ? 3 : 1) : ((MODE == 0 || MODE == 3) ? 1 : 2);
     static constexpr bool kStagger = ATB && MODE == 2;
     static constexpr int kChainKB = 4;  // tc_xb precise: K blocks per chain (48 accumulating MMAs)
 };
@@ -788,12 +828,29 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 if (warp == 0 && lane == 0) trace_ev(p, 5, it);
                 const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kASlotCols + mt * 32);
                 tmem_st16(a_addr, v);  // hi: the tensor core ignores the low 13 mantissa bits
+                if constexpr (kCrossEnabled && !ATB) {
+                    // cross operand, per K step of 8 values: 4 words of bf16 pairs of lo = v - tf32(v), then 4 words of bf16
+                    // pairs of v (K order [lo 0..7 | hi 0..7], matching the [hi ; lo] order of the B-side cross tile)
+                    uint32_t cw[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const float f = __uint_as_float(v[k]);
-                    v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
+                    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float f0 = __uint_as_float(v[8 * s2 + 2 * j]), f1 = __uint_as_float(v[8 * s2 + 2 * j + 1]);
+                            const float l0 = f0 - __uint_as_float(v[8 * s2 + 2 * j] & 0xFFFFE000u);
+                            const float l1 = f1 - __uint_as_float(v[8 * s2 + 2 * j + 1] & 0xFFFFE000u);
+                            cw[8 * s2 + j] = pack_bf16x2(l0, l1);
+                            cw[8 * s2 + 4 + j] = pack_bf16x2(f0, f1);
+                        }
+                    tmem_st16(a_addr + 16u, cw);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float f = __uint_as_float(v[k]);
+                        v[k] = __float_as_uint(f - __uint_as_float(v[k] & 0xFFFFE000u));
+                    }
+                    tmem_st16(a_addr + 16u, v);  // lo = v - tf32(v), exact
                 }
-                tmem_st16(a_addr + 16u, v);  // lo = v - tf32(v), exact
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -1058,6 +1115,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             // every address / descriptor is warp-uniform; only the tcgen05 instructions are elected.
             const int mt = warp - (kTransformWarps + 1);
             const uint32_t idesc = make_idesc_tf32(n_pad, 0);
+            const uint32_t idesc_x = make_idesc_bf16(n_pad);
             using MT_ = ModeTraits<ATB, MODE>;
             constexpr uint32_t aslots = (uint32_t)MT_::kSlots;
             constexpr int kAccBaseC = MT_::kAccBase;
@@ -1133,9 +1191,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                 const uint64_t dlo = dlo0 + (uint64_t)(ks * 2);
                                 const uint32_t a_hi = a_hi0 + (uint32_t)k2 * 8u;
                                 const uint32_t a_lo = a_hi + 16u;
-                                mma_tf32_ts(acc, a_lo, dhi, idesc, (!chain_start || ks > 0) ? 1u : 0u);
-                                mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
-                                mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
+                                if constexpr (kCrossEnabled && !ATB) {
+                                    // a_lo: this K step's 8 columns of bf16 [lo | hi]; dlo: the B-side cross tile [hi ; lo]
+                                    mma_tf32_ts(acc, a_hi, dhi, idesc, (!chain_start || ks > 0) ? 1u : 0u);
+                                    mma_f16_ts(acc, a_lo, dlo, idesc_x, 1u);
+                                } else {
+                                    mma_tf32_ts(acc, a_lo, dhi, idesc, (!chain_start || ks > 0) ? 1u : 0u);
+                                    mma_tf32_ts(acc, a_hi, dlo, idesc, 1u);
+                                    mma_tf32_ts(acc, a_hi, dhi, idesc, 1u);
+                                }
                             }
                             tc_commit(bar_a_free(bars, ta));
                             if (h == 1) {
@@ -1180,6 +1244,30 @@ __global__ void prep_b_kernel(const TS* __restrict__ B, int64_t ldb, int b_trans
     float h = __uint_as_float(__float_as_uint(bf) & 0xFFFFE000u);
     hi[idx] = h;
     lo[idx] = (float)(b - (double)h);
+}
+
+// cross mode: hi[n_pad][Kp] as above; xw[n_pad][Kp] 32-bit words - per group of 8 k values: 4 words of bf16 pairs of
+// hi, then 4 words of bf16 pairs of lo (the [hi ; lo] K order the A-side [lo | hi] operand is paired with)
+template <typename TS>
+__global__ void prep_b_cross_kernel(const TS* __restrict__ B, int64_t ldb, int b_trans, int64_t K, int64_t Kp, int L,
+                                    int n_pad, float* __restrict__ hi, uint32_t* __restrict__ xw) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per pair of k values
+    if (idx >= (int64_t)n_pad * (Kp / 2)) return;
+    const int64_t c = idx / (Kp / 2), kp = idx % (Kp / 2), k0 = 2 * kp;
+    float h[2], l[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int64_t k = k0 + e;
+        double b = 0.0;
+        if (c < L && k < K) b = (double)(b_trans ? B[c * ldb + k] : B[k * ldb + c]);
+        const float bf = (float)b;
+        h[e] = __uint_as_float(__float_as_uint(bf) & 0xFFFFE000u);
+        l[e] = (float)(b - (double)h[e]);
+        hi[c * Kp + k] = h[e];
+    }
+    const int64_t g = k0 >> 3, j = (k0 & 7) >> 1;
+    xw[c * Kp + 8 * g + j] = pack_bf16x2(h[0], h[1]);
+    xw[c * Kp + 8 * g + 4 + j] = pack_bf16x2(l[0], l[1]);
 }
 
 __global__ void prep_mu_kernel(const float* __restrict__ mu, int64_t K, int64_t Kp, float* __restrict__ out) {
@@ -1279,8 +1367,12 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     if (!pick_stages(false, n_pad, false, stages, stages_b)) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
     const int64_t Kp = round_up(K, 32);
     DBuf<float> bhi(ctx, (size_t)(n_pad * Kp)), blo(ctx, (size_t)(n_pad * Kp)), mup(ctx, (size_t)Kp);
-    prep_b_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * Kp, 256), 256, 0, ctx->stream>>>(B, ldb, b_trans ? 1 : 0, K, Kp,
-                                                                                            (int)L, n_pad, bhi.p, blo.p);
+    if (kCrossEnabled)
+        prep_b_cross_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * (Kp / 2), 256), 256, 0, ctx->stream>>>(
+            B, ldb, b_trans ? 1 : 0, K, Kp, (int)L, n_pad, bhi.p, reinterpret_cast<uint32_t*>(blo.p));
+    else
+        prep_b_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * Kp, 256), 256, 0, ctx->stream>>>(B, ldb, b_trans ? 1 : 0, K, Kp,
+                                                                                                (int)L, n_pad, bhi.p, blo.p);
     check_launch(ctx);
     prep_mu_kernel<<<(unsigned)ceil_div(Kp, 256), 256, 0, ctx->stream>>>(mu, K, Kp, mup.p);
     check_launch(ctx);
@@ -1310,11 +1402,17 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     const bool two_sets_fit = (n_pad <= 80);
     int mode = 0;
     if (two_sets_fit && want_precise(ctx, precise, "PETAL_XB_PRECISE")) mode = 2;
+    if (mode == 0 && n_pad <= 96) {  // 5 * 64 + 2 * n_pad <= 512
+        const char* e = getenv("PETAL_XB_SLOTS5");
+        if (e && atoi(e) != 0) mode = 3;  // opt-in: measured 5 % slower than the 4-slot ring on c2 (r02), kept for experiments
+    }
     const SmemLayout lay = make_layout(false, n_pad, stages, stages_b);
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
     KTimer kt(ctx, K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny", (double)n * (K + L) * sizeof(float));
     switch (mode * 2 + (y_panel ? 1 : 0)) {
+        case 6: launch_kernel<false, 0, false, 3>(ctx, p, grid, lay.total); break;
+        case 7: launch_kernel<false, 0, true, 3>(ctx, p, grid, lay.total); break;
         case 0: launch_kernel<false, 0, false, 0>(ctx, p, grid, lay.total); break;
         case 1: launch_kernel<false, 0, true, 0>(ctx, p, grid, lay.total); break;
         case 4: launch_kernel<false, 0, false, 2>(ctx, p, grid, lay.total); break;
