@@ -1,5 +1,7 @@
 """Summarises the ncu CSV pages collected by profiles/collect_ncu.sh (in gpurun_out/) into the tracked files
-profiles/r01_ncu_tc_kernels.txt, profiles/r01_ncu_launches_c2_2Mrows.txt and profiles/roofline_traffic.json."""
+profiles/<round>_ncu_tc_kernels.txt, profiles/<round>_ncu_launches_c2_2Mrows.txt, profiles/<round>_ncu_dmma_kernels.txt,
+profiles/<round>_ncu_launches_block_jacobi.txt and profiles/roofline_traffic.json.
+Usage: python profiles/summarize_ncu.py [gpurun_out] [round]"""
 import collections
 import csv
 import json
@@ -10,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, sys.argv[1] if len(sys.argv) > 1 else "gpurun_out")
 OUT = os.path.join(ROOT, "profiles")
-ROUND = "r01"
+ROUND = sys.argv[2] if len(sys.argv) > 2 else "r02"
 
 
 def raw(path):
@@ -40,11 +42,16 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "launch__block_size", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__shared_mem_per_block_dynamic"]
 
+WANT += ["sm__cycles_elapsed.avg.per_second", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+         "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+         "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 lines = ["# ncu --set full --clock-control none (profiles/collect_ncu.sh), raw page; " + ROUND,
          "# tc_gemm_kernel<ATB, NP, PANEL, MODE>: <0,0,1,0> = tc_xb fast, <0,0,1,2> = tc_xb precise, <1,80,1,2> = tc_atb precise"]
 agg = collections.defaultdict(list)
 for path, title in [("tc_full_raw.csv", "tc_gemm kernels, randomized PCA 2M x 1024 f32, l = 74 (first 11 launches of a fit)"),
                     ("ica_full_raw.csv", "ica_fused kernel, FastICA 1M x 64 f32")]:
+    if not os.path.exists(os.path.join(SRC, path)):
+        continue
     hdr, u, data = raw(os.path.join(SRC, path))
     lines.append("# " + title)
     for d in data:
@@ -75,12 +82,14 @@ def entry(kernel, note, alg_bytes, scale):
             "tensor_pipe_active_pct": mean(v, 2)}
 
 
+xb_key = [k for k in agg if k.startswith("tc_gemm_kernel<0, 0, 1, 0>") or k.startswith("tc_gemm_kernel<0, 0, 1, 3>")][0]
 traffic = {
+    "_round": ROUND,
     "_note": "DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch from one `ncu --set full` capture "
              "(profiles/collect_ncu.sh -> profiles/summarize_ncu.py); tc kernels at 2M x 1024 f32 rows, l = 74 "
              "(dram_bytes_per_launch scaled x5 to the 10M-row bench workload). Keys are bench.py's kernel names; bench.py "
              "uses `ratio`.",
-    "tc_xb_f32": entry("tc_gemm_kernel<0, 0, 1, 0>", "(fast mode; the precise last pass moves the same bytes)", alg, 5),
+    "tc_xb_f32": entry(xb_key, "(fast mode; the precise last pass moves the same bytes)", alg, 5),
     "tc_atb_f32": entry("tc_gemm_kernel<1, 80, 1, 2>", "(precise mode)", alg, 5),
 }
 ica = [k for k in agg if k.startswith("ica_fused")]
@@ -110,3 +119,43 @@ out = ["# ncu --metrics gpu__time_duration.sum --clock-control none (profiles/co
 for k, a in sorted(la.items(), key=lambda kv: -kv[1][1]):
     out.append("%-110s %4d %9.3f ms %5.1f %%" % (k[:110], a[0], a[1], 100 * a[1] / tot))
 open(os.path.join(OUT, ROUND + "_ncu_launches_c2_2Mrows.txt"), "w").write("\n".join(out) + "\n")
+
+
+# FP64 tensor-path kernels (exact PCA at c4s = 2M x 512): one big launch each
+dl = ["# ncu --set full --clock-control none (profiles/collect_ncu.sh), raw page; " + ROUND,
+      "# exact Pca f64 2M x 512 (bench.py --config c4s): first Gram launch (atb_dmma_kernel) and first pass-2 GEMM (gemm_nn_dmma_kernel)"]
+for path in ("dmma_gram_raw.csv", "dmma_gemm_raw.csv"):
+    fp = os.path.join(SRC, path)
+    if not os.path.exists(fp):
+        continue
+    hdr, u, data = raw(fp)
+    for d in data:
+        dl.append("---")
+        for k in WANT:
+            if k in d:
+                dl.append("  %-72s %s %s" % (k, d[k], u.get(k, "")))
+if len(dl) > 2:
+    open(os.path.join(OUT, ROUND + "_ncu_dmma_kernels.txt"), "w").write("\n".join(dl) + "\n")
+
+# launch list of the block Jacobi engine (2048 x 2048 SVD)
+fp = os.path.join(SRC, "launches_block_jacobi.csv")
+if os.path.exists(fp):
+    rows = list(csv.reader(open(fp)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]
+    data = [dict(zip(hdr, r)) for r in rows[hi + 1:] if len(r) == len(hdr)]
+    la = collections.OrderedDict()
+    for d in data:
+        if d.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", d["Kernel Name"])
+        a = la.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += toms(d["Metric Value"], d["Metric Unit"])
+    tot = sum(a[1] for a in la.values())
+    out = ["# ncu --metrics gpu__time_duration.sum --clock-control none: one-sided block Jacobi SVD of a 2048 x 2048 matrix "
+           "(tests/test_gpu_configs.py::test_block_jacobi_svd[2048-2048]); " + ROUND,
+           "# kernel, launches, total ms, share (serialised launches: compare shares)"]
+    for k, a in sorted(la.items(), key=lambda kv: -kv[1][1]):
+        out.append("%-110s %5d %9.3f ms %5.1f %%" % (k[:110], a[0], a[1], 100 * a[1] / tot))
+    open(os.path.join(OUT, ROUND + "_ncu_launches_block_jacobi.txt"), "w").write("\n".join(out) + "\n")
