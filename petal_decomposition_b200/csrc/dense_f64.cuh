@@ -486,6 +486,36 @@ bj_update_kernel(double* __restrict__ M, int64_t len, int nblk, int step, const 
 // 512 threads = 32 groups of 16 lanes, one group per pair of a round-robin step: rotation parameters, rows of G and J,
 // then columns of G (three barriers per step).
 // Row pitch me + 1 (odd): the column phase walks a column without bank conflicts.
+// Approximate rotation parameters for the block engine's inner solves: IEEE f64 divide / sqrt are ~40-instruction
+// dependent sequences and five of them per rotation are most of a step of the 64 x 64 kernel.  With a fixed, small
+// number of inner sweeps the tangent only has to be roughly right (the outer iteration recomputes the Gram matrices
+// and removes what is left: a 1e-6 residual of an off-diagonal that is already 1e-8 is below the tolerance), so it
+// is built from the MUFU reciprocal / rsqrt approximations; what has to be exact is c^2 + s^2 = 1 (J stays
+// orthogonal): the cosine is Newton-refined to full precision and s = c t.
+__device__ __forceinline__ double rcp_approx64(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ double rsqrt_approx64(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+__device__ __forceinline__ void rotation_from_approx(double alpha, double beta, double gamma, double& c, double& s) {
+    double zeta = (beta - alpha) * 0.5 * rcp_approx64(gamma);
+    zeta = fmin(fmax(zeta, -1e100), 1e100);
+    const double w = 1.0 + zeta * zeta;
+    double t = rcp_approx64(fabs(zeta) + w * rsqrt_approx64(w));
+    t = (zeta >= 0.0) ? t : -t;
+    const double x = 1.0 + t * t;  // in [1, 2]
+    double c0 = rsqrt_approx64(x);
+    c0 = c0 * (1.5 - 0.5 * x * c0 * c0);
+    c0 = c0 * (1.5 - 0.5 * x * c0 * c0);
+    c = c0;
+    s = c0 * t;
+}
+
 constexpr int kSymMaxM = 112;
 constexpr int kSymThreads = 512;
 inline size_t sym_jacobi_smem(int m) {
@@ -543,8 +573,13 @@ jacobi_sym_kernel(const double* __restrict__ Gin, int64_t g_stride, int m, doubl
                     rr_pair(me, step, pi, p, q);
                     if (q < m) {
                         const double al = Gs[p * LD + p], be = Gs[q * LD + q], ga = Gs[p * LD + q];
-                        if (al > floor_abs && be > floor_abs && fabs(ga) > tol * sqrt(al * be))
-                            rotation_from(al, be, ga, cc[u], ss[u], nullptr);
+                        if (sort) {  // stand-alone eigen-solver: exact parameters
+                            if (al > floor_abs && be > floor_abs && fabs(ga) > tol * sqrt(al * be))
+                                rotation_from(al, be, ga, cc[u], ss[u], nullptr);
+                        } else if (al > floor_abs && be > floor_abs) {
+                            const double prod = al * be;
+                            if (fabs(ga) > tol * (prod * rsqrt_approx64(prod))) rotation_from_approx(al, be, ga, cc[u], ss[u]);
+                        }
                     }
                 }
             }

@@ -201,11 +201,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 #define PETAL_TC_CROSS 1
 #endif
 constexpr bool kCrossEnabled = PETAL_TC_CROSS != 0;
-// Used by tc_xb (X B pass: 11.3 -> 9.0 ms at c2, same accuracy in every parity test).  tc_atb keeps the 3 x tf32 form:
-// its B-side cross tile would have to be derived from the fp32 Y panel by the splitter warp (per 8 values 2 LDS +
-// 16 ALU + 8 CVT + 2 STS), and one warp sharing its scheduler with four transform warps cannot do that within a
-// K block - measured (r02): X^T Y pass 10.7 -> 13.1 ms with one splitter warp, 18.9 ms with the X-producer warp as a
-// second splitter (its TMA issue then trails).
+#ifndef PETAL_TC_CROSS_ATB
+#define PETAL_TC_CROSS_ATB 0
+#endif
+// tc_atb with panel-major Y (build option, OFF): the B-side cross tile ([bf16 y | bf16 (y - tf32 y)] per K step) is
+// derived from the fp32 Y panel block by the sixteen transform warps, one 16 B chunk per thread, before they turn to
+// their own operand.  Correct (parity tests pass) but slower: tc_atb is bound by the instruction throughput of its
+// transform warps (transposing scalar shared-memory reads), not by the tensor pipe, and the cross operand adds to
+// exactly that - measured (r02, same box): X^T Y pass 10.9 -> 12.5 ms with this variant, 13.1 ms with a single
+// splitter warp, 18.9 ms with the X-producer warp as a second splitter.
+constexpr bool kCrossAtb = kCrossEnabled && (PETAL_TC_CROSS_ATB != 0);
+// Used by tc_xb (X B pass at c2: 11.3 -> 10.4 ms under the power cap, 1.93 -> 1.68 ms = 80 % of the HBM roofline in a
+// 2M-row burst; same accuracy in every parity test).  tc_atb keeps the 3 x tf32 form, see kCrossAtb.
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
     asm volatile(
@@ -719,6 +726,22 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
             if (!ATB && cut && pend_flush) flush_y(pend_row0);
             pend_on = false;
         };
+        // cross mode, tc_atb panel: the (up to two) 16 B chunks of the Y block this thread converts, loop invariant.
+        // Chunk e = (row n = e / 8, logical chunk c = e % 8) holds y[k = 4c .. 4c+3]; K step g = c / 2; its bf16 words go
+        // to bytes 8 (c % 2) .. of output chunk 2g (values) and 2g + 1 (low parts), all with the row's 128 B swizzle.
+        uint32_t yx_in[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, yx_hi[2] = {0, 0}, yx_lo[2] = {0, 0};
+        if (kCrossAtb && ATB && PANEL) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int e = ttid + u * kTransformWarps * 32;
+                if (e < NP * 8) {
+                    const int nrow = e >> 3, c = e & 7, sw = nrow & 7, g2 = c >> 1, hf = c & 1;
+                    yx_in[u] = (uint32_t)(nrow * 128 + ((c ^ sw) << 4));
+                    yx_hi[u] = (uint32_t)(nrow * 128 + (((2 * g2) ^ sw) << 4) + hf * 8);
+                    yx_lo[u] = (uint32_t)(nrow * 128 + (((2 * g2 + 1) ^ sw) << 4) + hf * 8);
+                }
+            }
+        }
         Group g;
         g.f0 = 0;
         RingPos rx(S), rb(p.stages_b), ry(kYBufs);
@@ -751,6 +774,29 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                     __syncwarp();  // smem X stage consumed (values are in registers)
                     if (lane == 0) mbar_arrive(bar_empty_x(bars, s));
                     if (warp == 0 && lane == 0) trace_ev(p, 7, it);
+                    if constexpr (kCrossAtb && PANEL) {
+                        // this thread's share of the B-side cross tile of the K block (see kCrossAtb)
+                        const int sbq = rb.s;
+                        mbar_wait(bar_full_b(bars, sbq), rb.ph);
+                        const uint8_t* bh8 = base_ptr + L.bhi + (uint32_t)sbq * L.stage_b;
+                        uint8_t* bl8 = base_ptr + L.blo + (uint32_t)sbq * L.stage_b;
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (yx_in[u] != 0xFFFFFFFFu) {
+                                const float4 y = *reinterpret_cast<const float4*>(bh8 + yx_in[u]);
+                                const float l0 = y.x - __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u);
+                                const float l1 = y.y - __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
+                                const float l2 = y.z - __uint_as_float(__float_as_uint(y.z) & 0xFFFFE000u);
+                                const float l3 = y.w - __uint_as_float(__float_as_uint(y.w) & 0xFFFFE000u);
+                                *reinterpret_cast<uint2*>(bl8 + yx_hi[u]) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                                *reinterpret_cast<uint2*>(bl8 + yx_lo[u]) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_full_b2(bars, sbq));
+                        rb.advance();
+                    }
                 } else {
                     // tile [256 rows][32 floats], 128 B rows, SWIZZLE_128B: this thread owns one row and
                     // the 16 B chunks 4*half .. 4*half+3 of it
@@ -828,7 +874,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 if (warp == 0 && lane == 0) trace_ev(p, 5, it);
                 const uint32_t a_addr = tmem_base + lane_field + (uint32_t)(ta * kASlotCols + mt * 32);
                 tmem_st16(a_addr, v);  // hi: the tensor core ignores the low 13 mantissa bits
-                if constexpr (kCrossEnabled && !ATB) {
+                if constexpr ((kCrossEnabled && !ATB) || (kCrossAtb && ATB && PANEL)) {
                     // cross operand, per K step of 8 values: 4 words of bf16 pairs of lo = v - tf32(v), then 4 words of bf16
                     // pairs of v (K order [lo 0..7 | hi 0..7], matching the [hi ; lo] order of the B-side cross tile)
                     uint32_t cw[16];
@@ -964,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
         for (int s = 0; s < SB; ++s) {
             mbar_init(bar_full_b(bars, s), 1);
-            mbar_init(bar_full_b2(bars, s), 1);
+            mbar_init(bar_full_b2(bars, s), (kCrossAtb && ATB && panel) ? kTransformWarps : 1);
             // released by the two MMA warps, or by the transform warps when they consume the raw row-major Y tile
             mbar_init(bar_empty_b(bars, s), (ATB && !panel) ? kTransformWarps : kMT);
         }
@@ -1004,6 +1050,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 mbar_expect_tx(fullb, L.stage_b);
                 tma_load_2d(base + L.bhi + (uint32_t)stage * L.stage_b, &p.map_bhi, 0, (int)(r / 32) * n_pad, fullb);
             };
+            if constexpr (kCrossAtb) {
+                // cross mode: the transform warps derive the second operand tile; this warp only keeps the B ring full
+                if (lane == 0) {
+                    RingPos rp(SB);
+                    for (uint32_t blk = 0; blk < total; ++blk, rp.advance()) {
+                        mbar_wait_relaxed(bar_empty_b(bars, rp.s), rp.ph ^ 1u, 64);
+                        load_block(blk, rp.s);
+                    }
+                }
+            } else {
             if (lane == 0)
                 for (uint32_t i = 0; i < total && i < (uint32_t)SB; ++i) load_block(i, (int)i);
             RingPos rb(SB), rr(SB);  // block being split / stage being refilled (one block behind)
@@ -1045,6 +1101,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     rr.advance();
                     __syncwarp();
                 }
+            }
             }
         } else if (warp == kTransformWarps) {
             // ================================ TMA producer: X ring ================================
@@ -1191,7 +1248,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                 const uint64_t dlo = dlo0 + (uint64_t)(ks * 2);
                                 const uint32_t a_hi = a_hi0 + (uint32_t)k2 * 8u;
                                 const uint32_t a_lo = a_hi + 16u;
-                                if constexpr (kCrossEnabled && !ATB) {
+                                if constexpr ((kCrossEnabled && !ATB) || (kCrossAtb && ATB && PANEL)) {
                                     // a_lo: this K step's 8 columns of bf16 [lo | hi]; dlo: the B-side cross tile [hi ; lo]
                                     mma_tf32_ts(acc, a_hi, dhi, idesc, (!chain_start || ks > 0) ? 1u : 0u);
                                     mma_f16_ts(acc, a_lo, dlo, idesc_x, 1u);
@@ -1443,7 +1500,7 @@ inline void launch_tc_atb(petal_ctx* ctx, const float* A, int64_t lda, int64_t d
     p.map_x = make_map_2d(A, (uint64_t)da, (uint64_t)n, (uint64_t)lda, 32, 32, true);
     if (b_panel) {
         p.map_bhi = make_map_2d(B, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
-        p.b_split = (B_lo_panel == nullptr) ? 1 : 0;  // no Y_lo panel: the operand tile is derived inside the kernel
+        p.b_split = (B_lo_panel == nullptr || kCrossAtb) ? 1 : 0;  // no Y_lo panel: the operand tile is derived inside the kernel
         p.map_blo = p.b_split ? p.map_bhi
                               : make_map_2d(B_lo_panel, 32, (uint64_t)ceil_div(n, 32) * (uint64_t)n_pad, 32, 32, (uint32_t)n_pad, true);
     } else {
