@@ -520,7 +520,7 @@ def main():
             top = max(stream_k, key=lambda kn: stream_k[kn]["total_ms"])
             v = stream_k[top]
             all_ms = {kn: round(vv["total_ms"] / args.steps, 4) for kn, vv in prof.items()}
-            if top in ("atb_dmma_f64", "gemm_dmma_f64", "syrk_dmma_f64"):
+            if top in ("atb_dmma_f64", "gemm_dmma_f64", "syrk_dmma_f64") and v["total_ms"] / v["count"] > 1.0:
                 # FP64 tensor pipe: the Gram passes of exact PCA at d >= ~256 are compute-bound (AI ~ d/8 flop/B);
                 # flops syrk-counted as SURVEY 8(d): d (d + 1) per sample and pass
                 # rows are summed over the launches through `work` (= rows x d x 8 bytes for a symmetric Gram launch)

@@ -27,6 +27,8 @@ pub enum DecompositionError {
 }
 
 struct Ctx(*mut ffi::PetalCtx);
+// libpetal_b200 serialises calls on one context with an internal mutex (one call at a time per context, like the
+// reference's `&mut self` on fit), so sharing the handle between threads is sound.
 unsafe impl Send for Ctx {}
 unsafe impl Sync for Ctx {}
 
