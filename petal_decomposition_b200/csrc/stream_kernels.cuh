@@ -1002,19 +1002,140 @@ panel_xb_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const fl
     }
 }
 
+// Register-tiled variant for k <= 4 * CG (CG = 8, 16): each thread owns 8 consecutive rows x 4 consecutive columns
+// (per panel column c: two broadcast LDS.128 of Y, one LDS.128 of S, 32 FFMA - the 8 x KV tiling above spends as many
+// cycles on shared-memory loads as on FFMAs).  256 threads = CG column groups x (256 / CG) row groups: tiles of
+// 128 (CG = 16) or 256 (CG = 8) rows.
+template <int CG>
+__global__ void __launch_bounds__(256)
+panel_xb4_kernel(const float* __restrict__ Yp, int64_t n, int np, int l, const float* __restrict__ S, int k,
+                 float* __restrict__ out /* nullable */, int64_t ldo, AbsMax* __restrict__ partial /* nullable */) {
+    extern __shared__ float psm[];
+    constexpr int RG = 256 / CG, ROWS = RG * 8, NB = ROWS / 32, TS = ROWS + 4, KP = 4 * CG;
+    float* Ss = psm;                   // [l][KP]
+    float* Ts = psm + (size_t)l * KP;  // [np][TS]: column c of the tile's rows at c*TS + i
+    const int tid = threadIdx.x;
+    for (int e = tid; e < l * KP; e += 256) {
+        const int c = e / KP, j = e % KP;
+        Ss[e] = (j < k) ? S[c * k + j] : 0.f;
+    }
+    const int64_t nblocks = (n + 31) / 32;
+    const int64_t ntiles = (nblocks + NB - 1) / NB;
+    const int cg = tid % CG, rg = tid / CG;
+    float best_a[4], best_s[4];
+    int64_t best_i[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        best_a[v] = -1.f;
+        best_s[v] = 1.f;
+        best_i[v] = INT64_MAX;
+    }
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int64_t blk = t * NB + b;
+            const float* src = Yp + blk * np * 32;
+            if (blk < nblocks) {
+                for (int e = tid; e < np * 32; e += 256) Ts[(e >> 5) * TS + b * 32 + (e & 31)] = src[e];
+            } else {
+                for (int e = tid; e < np * 32; e += 256) Ts[(e >> 5) * TS + b * 32 + (e & 31)] = 0.f;
+            }
+        }
+        __syncthreads();
+        float acc[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+#pragma unroll 2
+        for (int c = 0; c < l; ++c) {
+            const float4 y0 = *reinterpret_cast<const float4*>(Ts + c * TS + 8 * rg);
+            const float4 y1 = *reinterpret_cast<const float4*>(Ts + c * TS + 8 * rg + 4);
+            const float4 s4 = *reinterpret_cast<const float4*>(Ss + c * KP + 4 * cg);
+            const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(y[u], sv[v], acc[u][v]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t r = t * ROWS + 8 * rg + u;
+            if (r < n) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v)
+                    if (4 * cg + v < k) {
+                        if (out != nullptr) out[r * ldo + 4 * cg + v] = acc[u][v];
+                        const float a = fabsf(acc[u][v]);  // rows increase: a strict > keeps the first maximum
+                        if (a > best_a[v]) {
+                            best_a[v] = a;
+                            best_s[v] = acc[u][v];
+                            best_i[v] = r;
+                        }
+                    }
+            }
+        }
+    }
+    if (partial != nullptr) {
+        __syncthreads();
+        AbsMax* red = reinterpret_cast<AbsMax*>(psm);  // [RG][KP]
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            AbsMax b;
+            b.a = (double)best_a[v];
+            b.sgn = signbit(best_s[v]) ? -1.0 : 1.0;
+            b.idx = best_i[v];
+            red[rg * KP + 4 * cg + v] = b;
+        }
+        __syncthreads();
+        if (rg == 0) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const int col = 4 * cg + v;
+                if (col < k) {
+                    AbsMax b = red[col];
+                    for (int y = 1; y < RG; ++y) {
+                        const AbsMax c2 = red[y * KP + col];
+                        if (absmax_better(c2, b)) b = c2;
+                    }
+                    partial[(int64_t)blockIdx.x * k + col] = b;
+                }
+            }
+        }
+    }
+}
+
 // out (n x k, row-major) may be null when only absmax3 (k x 3: |max|, first local row, sign) is wanted
 inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, int l, const float* S, int k,
                             float* out, int64_t ldo, double* absmax3 = nullptr) {
     if (n == 0 || k == 0) return;
+    const int64_t nblocks = ceil_div(n, 32);
+    const char* tile_env = getenv("PETAL_PANEL_XB4");
+    const bool tiled = k <= 64 && !(tile_env && atoi(tile_env) == 0);
+    DBuf<AbsMax> partial;
+    int grid = 0;
+    if (tiled) {
+        const int cgn = k <= 32 ? 8 : 16, rows = (256 / cgn) * 8, kp = 4 * cgn;
+        size_t smem = ((size_t)l * kp + (size_t)np * (rows + 4)) * sizeof(float);
+        smem = std::max(smem, (size_t)(256 / cgn) * kp * sizeof(AbsMax));
+        ensure_dynamic_smem(ctx, panel_xb4_kernel<8>, 160 * 1024);
+        ensure_dynamic_smem(ctx, panel_xb4_kernel<16>, 160 * 1024);
+        grid = (int)std::min<int64_t>(ceil_div(nblocks, rows / 32), (int64_t)ctx->sm_count * 3);
+        if (absmax3 != nullptr) partial.alloc(ctx, (size_t)grid * k);
+        KTimer kt(ctx, "panel_xb_f32", (double)n * (np + (out ? k : 0)) * sizeof(float));
+        if (cgn == 8) panel_xb4_kernel<8><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
+        else panel_xb4_kernel<16><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
+        check_launch(ctx);
+    } else {
     const int kv = k <= 32 ? 1 : (k <= 64 ? 2 : 4);
     size_t smem = ((size_t)l * 32 * kv + 68 * (size_t)np) * sizeof(float);
     ensure_dynamic_smem(ctx, panel_xb_kernel<1>, 100 * 1024);
     ensure_dynamic_smem(ctx, panel_xb_kernel<2>, 100 * 1024);
     ensure_dynamic_smem(ctx, panel_xb_kernel<4>, 100 * 1024);
-    const int64_t nblocks = ceil_div(n, 32);
-    const int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->sm_count * 4);
+    grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->sm_count * 4);
     smem = std::max(smem, (size_t)8 * 32 * kv * sizeof(AbsMax));
-    DBuf<AbsMax> partial;
     if (absmax3 != nullptr) partial.alloc(ctx, (size_t)grid * k);
     {
         KTimer kt(ctx, "panel_xb_f32", (double)n * (np + (out ? k : 0)) * sizeof(float));
@@ -1022,6 +1143,7 @@ inline void launch_panel_xb(petal_ctx* ctx, const float* Yp, int64_t n, int np, 
         else if (k <= 64) panel_xb_kernel<2><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
         else panel_xb_kernel<4><<<grid, 256, smem, ctx->stream>>>(Yp, n, np, l, S, k, out, ldo, partial.p);
         check_launch(ctx);
+    }
     }
     if (absmax3 != nullptr) {
         colabsmax_final_kernel<<<(unsigned)ceil_div(k, 128), 128, 0, ctx->stream>>>(partial.p, grid, k, absmax3);

@@ -173,3 +173,26 @@ def test_serde_wire_format_round_trip(lib):
     assert np.array_equal(i2.components, ica.components) and np.array_equal(i2.means, ica.means) and i2.n_iter == 3
     with pytest.raises(pd.InvalidInput):
         pd.Pca.from_json(text.replace('"dim":[1,2]', '"dim":[3,2]'), np.float32)
+
+
+def test_folded_mean_algebra():
+    """The rank-one corrections petal_rpca_fit applies when the column means are folded into the first two
+    range-finder passes: products taken with a provisional mean mu~ plus the column sums of
+    X - mu~ give the exactly centred quantities."""
+    rng = np.random.default_rng(3)
+    n, d, l = 500, 12, 5
+    x = rng.standard_normal((n, d)) * rng.uniform(0.5, 3, d) + rng.uniform(-4, 4, d)
+    omega = rng.standard_normal((d, l))
+    mu_t = x[:64].mean(axis=0)                      # provisional mean from a row sample
+    xt = x - mu_t
+    yt = xt @ omega                                 # X Omega pass with mu~
+    zt = xt.T @ np.hstack([yt, np.ones((n, 1))])    # X^T [Y | 1] pass: last column = column sums of X - mu~
+    c = zt[:, l]
+    delta = c / n
+    w, u = omega.T @ delta, omega.T @ c
+    z = zt[:, :l] - np.outer(c, w) - np.outer(delta, u) + n * np.outer(delta, w)
+    tv = np.sum(xt * xt) - 2 * delta @ c + n * delta @ delta
+    xc = x - x.mean(axis=0)
+    assert np.allclose(mu_t + delta, x.mean(axis=0), rtol=0, atol=1e-13)
+    assert np.allclose(z, xc.T @ (xc @ omega), rtol=1e-12, atol=1e-9)
+    assert np.isclose(tv, np.sum(xc * xc), rtol=1e-12)
