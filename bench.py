@@ -57,6 +57,10 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (testing only)")
     ap.add_argument("--engine", type=int, default=-1, help="f32 engine: 0 SIMT, 1 tcgen05 (default: library default)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-staging", type=int, default=0, choices=[0, 1, 2],
+                    help="e2e arm: how the host X reaches HBM - 0 resident copy when it fits (chunks consumed as they land), "
+                         "1 always resident, 2 out-of-core (X re-streamed through a two-slot ring by every traversal)")
+    ap.add_argument("--host-chunk-mb", type=int, default=0, help="e2e arm: H2D chunk size (default: the library's 1 GiB)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
@@ -477,6 +481,7 @@ def main():
             del x
             torch.cuda.empty_cache()
             ctx.trim()
+            ctx.set_host_staging(args.host_staging, args.host_chunk_mb << 20)
             for _ in range(min(args.warmup, 1)):
                 step(xh)
             barrier()
@@ -496,6 +501,12 @@ def main():
                    "d2h_bytes_per_step": int(d2h), "rows_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
                    "numa_bound_cpus": numa_cpus,
                    "timing": "wall clock around the public API call (includes H2D of X from pinned host memory)"}
+            st = ctx.host_stream_stats()
+            e2e["host_staging"] = {"mode": "out-of-core ring" if st["out_of_core"] else "resident copy, chunks consumed as they land",
+                                   "traversals_of_x": st["traversals"], "h2d_bytes_moved": st["h2d_bytes"],
+                                   "chunk_bytes": (args.host_chunk_mb << 20) or (1 << 30)}
+            if st["out_of_core"]:
+                e2e["h2d_bytes_per_step"] = int(st["h2d_bytes"])
         except Exception as e:  # host memory too small etc.
             e2e = {"value": None, "unit": "samples/s", "error": str(e)[:200]}
 

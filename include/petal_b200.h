@@ -71,6 +71,21 @@ int petal_ctx_set_f32_engine(petal_ctx* ctx, int engine);
 /* Same for f64 Gram-shaped contractions: 0 = SIMT DFMA kernels, 1 = DMMA (mma.sync.m8n8k4.f64, default). */
 int petal_ctx_set_f64_engine(petal_ctx* ctx, int engine);
 
+/* Host-resident X (out-of-core / streaming ingest).  A host `x` passed to a fit / transform entry is
+ * copied to HBM in row chunks of about `chunk_bytes` (default 1 GiB; <= 0 keeps the current value) on a second stream,
+ * double-buffered, and each chunk is consumed as soon as it has landed (pinned host memory makes the copies
+ * asynchronous; pageable memory works, without overlap).
+ *   mode 0 (default): keep a resident copy when X fits into the free HBM next to the call's workspaces - the first
+ *          streaming pass of the fit then runs underneath the transfer - otherwise
+ *   mode 2: out-of-core: X is re-streamed through a two-slot ring by every traversal; the flows pair the two
+ *          contractions of a range-finder iteration on the resident chunk (q + 1 trips over PCIe for randomized PCA,
+ *          3 for exact PCA with scores, 2 + iterations for FastICA).  mode 1 forces the resident copy.
+ * A host `out` of inverse_transform larger than a chunk is produced and drained chunk by chunk in the same way.
+ * Returns the mode now in force (negative `mode` only queries). */
+int petal_ctx_set_host_staging(petal_ctx* ctx, int mode, int64_t chunk_bytes);
+/* What the last call that was given a host X did: bytes copied host->device, traversals of X, ring (1) or resident (0). */
+int petal_ctx_host_stream_stats(const petal_ctx* ctx, int64_t* h2d_bytes, int64_t* traversals, int* ring);
+
 /* ---- multi-GPU (row sharding; replaces nothing in the reference, which is single-host) - */
 #define PETAL_COMM_ID_BYTES 128
 /* Rank 0 creates an NCCL unique id and ships it to the other ranks (torch.distributed / MPI). */
@@ -161,6 +176,18 @@ int petal_fastica_fit_f64(petal_ctx* ctx, const double* x, int64_t n, int64_t d,
                           int64_t max_iter, int lim_variant, const double* w_init, double* components,
                           double* mean, int64_t* n_iter, double* final_lim, double* sources);
 
+/* Deflation scheme (not in the reference, which only has the symmetric scheme above): the
+ * components are extracted one at a time by the one-unit fixed-point iteration with Gram-Schmidt against the finished
+ * ones - sklearn `_ica_def` (_fastica.py:65-100), restated in oracle/ica.py.  Same whitening (src/ica.rs:189-208),
+ * contrast functions and outputs as petal_fastica_fit_*; n_iter = the largest iteration count over the components,
+ * final_lim = the largest final | |<w+, w>| - 1 |.  One pass over X per iteration (d * sizeof(T) bytes per sample). */
+int petal_fastica_deflation_fit_f32(petal_ctx* ctx, const float* x, int64_t n, int64_t d, int fun, double tol,
+                                    int64_t max_iter, const float* w_init, float* components, float* mean,
+                                    int64_t* n_iter, double* final_lim, float* sources);
+int petal_fastica_deflation_fit_f64(petal_ctx* ctx, const double* x, int64_t n, int64_t d, int fun, double tol,
+                                    int64_t max_iter, const double* w_init, double* components, double* mean,
+                                    int64_t* n_iter, double* final_lim, double* sources);
+
 /* ---- building blocks exposed for unit tests (tests/ call these through the same ABI) -----
  * ica_par (src/ica.rs:319-361) on an already-whitened nc x n matrix given as its transpose
  * x1t[n*nc] (samples x components, row-major); w_init / w_out[nc*nc] are f64 for both data types (the small
@@ -171,6 +198,12 @@ int petal_ica_par_f32(petal_ctx* ctx, const float* x1t, int64_t n, int64_t nc, i
 int petal_ica_par_f64(petal_ctx* ctx, const double* x1t, int64_t n, int64_t nc, int fun, double tol,
                       int64_t max_iter, int lim_variant, const double* w_init, double* w_out,
                       int64_t* n_iter, double* final_lim);
+/* The deflation scheme on an already-whitened matrix (same conventions as petal_ica_par_*): replays sklearn's
+ * `_ica_def` golden vectors (tests/golden/ica_deflation.json). */
+int petal_ica_defl_f32(petal_ctx* ctx, const float* x1t, int64_t n, int64_t nc, int fun, double tol, int64_t max_iter,
+                       const double* w_init, double* w_out, int64_t* n_iter, double* final_lim);
+int petal_ica_defl_f64(petal_ctx* ctx, const double* x1t, int64_t n, int64_t nc, int fun, double tol, int64_t max_iter,
+                       const double* w_init, double* w_out, int64_t* n_iter, double* final_lim);
 /* logcosh (src/ica.rs:383-398) and the exp / cube extensions, elementwise: u[n*nc] (samples x components) is
  * replaced by g(u), gprime_sum[nc] = sum over the n samples of g'(u) (the reference divides by n).
  * engine 0: the kernel of the generic path (libm-accurate tanh / exp); engine 1 (f32 only): the device function

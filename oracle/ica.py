@@ -93,14 +93,45 @@ def ica_par(x1: np.ndarray, tol: float, max_iter: int, w_init: np.ndarray,
     return w, max_iter
 
 
+def ica_def(x1: np.ndarray, tol: float, max_iter: int, w_init: np.ndarray, fun: str = "logcosh"):
+    """Deflation FastICA: sklearn `_ica_def` (sklearn/decomposition/_fastica.py:65-100; `_gs_decorrelation` :38-62).
+    Not in the reference (src/ica.rs has the symmetric scheme only) - SURVEY 8(f) rank 4.  x1 is nc x n (whitened).
+    Pinned against sklearn's own function by tests/golden/ica_deflation.json (tests/golden/make_ica_deflation_fixture.py).
+    Returns (W, largest iteration count over the components)."""
+    g = G_FUNS[fun]
+    nc = w_init.shape[0]
+    w_all = np.zeros((nc, nc), dtype=x1.dtype)
+    n_iter = []
+    for j in range(nc):
+        w = w_init[j, :].copy()
+        w /= np.sqrt((w ** 2).sum())  # _fastica.py:79-80
+        i = 0
+        for i in range(max_iter):
+            gwtx, g_wtx = g((w @ x1)[None, :])  # :83
+            w1 = (x1 * gwtx[0]).mean(axis=1) - g_wtx[0] * w  # :85
+            w1 -= (w1 @ w_all[:j].T) @ w_all[:j]  # _gs_decorrelation, :60-61
+            w1 /= np.sqrt((w1 ** 2).sum())  # :89
+            lim = np.abs(np.abs((w1 * w).sum()) - 1)  # :91
+            w = w1
+            if lim < tol:  # :93-94
+                break
+        n_iter.append(i + 1)
+        w_all[j, :] = w
+    return w_all, max(n_iter)
+
+
 class FastIca:
-    """reference src/ica.rs:41-222. `rng` is an oracle.rng.Mcg128Xsl64 or pass w_init."""
+    """reference src/ica.rs:41-222. `rng` is an oracle.rng.Mcg128Xsl64 or pass w_init.
+    algorithm="deflation" swaps ica_par for ica_def (extension, see ica_def)."""
 
     TOL = 1e-4  # ica.rs:216
     MAX_ITER = 200
 
-    def __init__(self, rng=None, symdec="textbook", lim="rowrow", max_iter=None, tol=None):
+    def __init__(self, rng=None, symdec="textbook", lim="rowrow", max_iter=None, tol=None, algorithm="parallel",
+                 fun="logcosh"):
         self.rng = rng
+        self.algorithm = algorithm
+        self.fun = fun
         self.symdec = symdec
         self.lim = lim
         self.max_iter = self.MAX_ITER if max_iter is None else max_iter
@@ -124,8 +155,11 @@ class FastIca:
         x1 = (k @ xt) * x.dtype.type(np.sqrt(x.dtype.type(n)))  # ica.rs:204-208
         if w_init is None:
             w_init = self.rng.normal_matrix(nc, nc, x.dtype)  # ica.rs:210-214
-        w, n_iter = ica_par(x1, x.dtype.type(self.tol), self.max_iter, w_init.astype(x.dtype),
-                            self.symdec, self.lim)
+        if self.algorithm == "deflation":
+            w, n_iter = ica_def(x1, x.dtype.type(self.tol), self.max_iter, w_init.astype(x.dtype), self.fun)
+        else:
+            w, n_iter = ica_par(x1, x.dtype.type(self.tol), self.max_iter, w_init.astype(x.dtype),
+                                self.symdec, self.lim, self.fun)
         self.components = w @ k  # ica.rs:217
         self.means = means
         self.n_iter = n_iter

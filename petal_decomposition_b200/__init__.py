@@ -9,14 +9,14 @@ from . import _cabi
 
 _cabi.load()  # no CPU fallback: the CUDA library must exist
 
-from .api import (CUBE, EXP, LOGCOSH, Context, DecompositionError, FastIca, FastIcaBuilder,  # noqa: E402,F401
+from .api import (CUBE, DEFLATION, EXP, LOGCOSH, PARALLEL, Context, DecompositionError, FastIca, FastIcaBuilder,  # noqa: E402,F401
                   InvalidInput, LinalgError, Pca, PcaBuilder, Pcg, RandomizedPca, RandomizedPcaBuilder,
-                  colmean_gram, default_context, ica_par, logcosh, set_default_context, small_svd,
+                  colmean_gram, default_context, ica_def, ica_par, logcosh, set_default_context, small_svd,
                   symmetric_decorrelation, xty)
 
 __all__ = [
     "Pca", "PcaBuilder", "RandomizedPca", "RandomizedPcaBuilder", "FastIca", "FastIcaBuilder",
     "DecompositionError", "InvalidInput", "LinalgError", "Pcg", "Context", "default_context",
-    "set_default_context", "ica_par", "logcosh", "symmetric_decorrelation", "small_svd", "colmean_gram", "xty",
-    "LOGCOSH", "EXP", "CUBE",
+    "set_default_context", "ica_par", "ica_def", "logcosh", "symmetric_decorrelation", "small_svd", "colmean_gram", "xty",
+    "LOGCOSH", "EXP", "CUBE", "PARALLEL", "DEFLATION",
 ]

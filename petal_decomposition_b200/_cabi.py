@@ -22,6 +22,8 @@ _TYPED = {
     "petal_inverse_transform": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "petal_fastica_fit": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_int, c_vp, c_vp, c_vp,
                                   C.POINTER(c_i64), C.POINTER(c_dbl), c_vp]),
+    "petal_fastica_deflation_fit": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_vp, c_vp, c_vp,
+                                            C.POINTER(c_i64), C.POINTER(c_dbl), c_vp]),
     "petal_colmean_gram": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "petal_xty": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "petal_ica_nonlin": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_vp]),
@@ -37,6 +39,8 @@ SYMBOLS = {
     "petal_ctx_launch_count": (c_i64, [c_vp]),
     "petal_ctx_set_f32_engine": (c_int, [c_vp, c_int]),
     "petal_ctx_set_f64_engine": (c_int, [c_vp, c_int]),
+    "petal_ctx_set_host_staging": (c_int, [c_vp, c_int, c_i64]),
+    "petal_ctx_host_stream_stats": (c_int, [c_vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_int)]),
     "petal_ctx_set_profiling": (c_int, [c_vp, c_int]),
     "petal_ctx_profile_json": (c_i64, [c_vp, C.c_char_p, c_i64]),
     "petal_comm_unique_id": (c_int, [c_vp]),
@@ -52,6 +56,10 @@ SYMBOLS = {
                                   C.POINTER(c_i64), C.POINTER(c_dbl)]),
     "petal_ica_par_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_int, c_vp, c_vp,
                                   C.POINTER(c_i64), C.POINTER(c_dbl)]),
+    "petal_ica_defl_f32": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_vp, c_vp,
+                                   C.POINTER(c_i64), C.POINTER(c_dbl)]),
+    "petal_ica_defl_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_dbl, c_i64, c_vp, c_vp,
+                                   C.POINTER(c_i64), C.POINTER(c_dbl)]),
     "petal_symmetric_decorrelation_f64": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "petal_probe_dmma_tflops": (c_int, [c_vp, c_int, c_vp]),
     "petal_small_svd_f64": (c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),

@@ -101,6 +101,19 @@ class Context:
     def set_f32_engine(self, engine: int) -> int:
         return int(self.lib.petal_ctx_set_f32_engine(self.handle, int(engine)))
 
+    RESIDENT_IF_FITS, RESIDENT, OUT_OF_CORE = 0, 1, 2
+
+    def set_host_staging(self, mode: int = -1, chunk_bytes: int = 0) -> int:
+        """How a host (numpy) X reaches HBM: 0 = resident copy when it fits, else out-of-core; 1 = always resident;
+        2 = always out-of-core (X re-streamed through a two-slot ring by every pass).  chunk_bytes: H2D chunk size."""
+        return int(self.lib.petal_ctx_set_host_staging(self.handle, int(mode), int(chunk_bytes)))
+
+    def host_stream_stats(self) -> dict:
+        """H2D bytes, traversals of X and the mode of the last call that was given a host X."""
+        b, t, r = C.c_int64(0), C.c_int64(0), C.c_int(0)
+        self.check(self.lib.petal_ctx_host_stream_stats(self.handle, C.byref(b), C.byref(t), C.byref(r)))
+        return {"h2d_bytes": int(b.value), "traversals": int(t.value), "out_of_core": bool(r.value)}
+
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, _cabi.COMM_ID_BYTES)
         self.check(self.lib.petal_comm_init(self.handle, buf, int(rank), int(world)))
@@ -596,6 +609,7 @@ class RandomizedPcaBuilder:
 
 
 LOGCOSH, EXP, CUBE = 0, 1, 2
+PARALLEL, DEFLATION = "parallel", "deflation"
 
 
 class FastIca:
@@ -606,9 +620,14 @@ class FastIca:
     here.  tol / max_iter default to the constants at src/ica.rs:216."""
 
     def __init__(self, rng: Pcg | None = None, fun: int = LOGCOSH, tol: float = 1e-4, max_iter: int = 200,
-                 lim_variant: int = 0, ctx: Context | None = None):
+                 lim_variant: int = 0, ctx: Context | None = None, algorithm: str = PARALLEL):
+        if algorithm not in (PARALLEL, DEFLATION):
+            raise InvalidInput("algorithm must be 'parallel' or 'deflation'")
         self.rng = rng if rng is not None else Pcg.from_entropy()
         self.fun, self.tol, self.max_iter, self.lim_variant = fun, tol, max_iter, lim_variant
+        # 'parallel' = the reference's symmetric scheme (src/ica.rs:319-361); 'deflation' = one component at a time
+        # (extension, SURVEY 8(f); sklearn `_ica_def`)
+        self.algorithm = algorithm
         self._ctx = ctx
         self.components = np.zeros((0, 0))  # src/ica.rs:66-72
         self.means = np.zeros(0)
@@ -651,10 +670,15 @@ class FastIca:
         mean = np.empty(d, dtype=a.dtype)
         n_iter, lim = C.c_int64(0), C.c_double(0.0)
         sources, sptr = a.empty_like_kind((n, nc)) if want_sources else (None, C.c_void_p(0))
-        fn = getattr(ctx.lib, f"petal_fastica_fit_{a.suffix}")
-        ctx.check(fn(ctx.handle, a.ptr, n, d, self.fun, float(self.tol), int(self.max_iter),
-                     int(self.lim_variant), _np_ptr(w_init), _np_ptr(comps), _np_ptr(mean), C.byref(n_iter),
-                     C.byref(lim), sptr))
+        if self.algorithm == DEFLATION:
+            fn = getattr(ctx.lib, f"petal_fastica_deflation_fit_{a.suffix}")
+            ctx.check(fn(ctx.handle, a.ptr, n, d, self.fun, float(self.tol), int(self.max_iter), _np_ptr(w_init),
+                         _np_ptr(comps), _np_ptr(mean), C.byref(n_iter), C.byref(lim), sptr))
+        else:
+            fn = getattr(ctx.lib, f"petal_fastica_fit_{a.suffix}")
+            ctx.check(fn(ctx.handle, a.ptr, n, d, self.fun, float(self.tol), int(self.max_iter),
+                         int(self.lim_variant), _np_ptr(w_init), _np_ptr(comps), _np_ptr(mean), C.byref(n_iter),
+                         C.byref(lim), sptr))
         self.components, self.means = comps, mean
         self.n_iter, self.final_lim = int(n_iter.value), float(lim.value)
         return sources
@@ -696,6 +720,7 @@ class FastIcaBuilder:
     def __init__(self, rng: Pcg | None = None):
         self._rng = rng
         self._fun = LOGCOSH
+        self._algorithm = PARALLEL
 
     @classmethod
     def new(cls) -> "FastIcaBuilder":
@@ -713,8 +738,12 @@ class FastIcaBuilder:
         self._fun = fun
         return self
 
+    def algorithm(self, algorithm: str) -> "FastIcaBuilder":  # extension: 'deflation' (the reference is 'parallel')
+        self._algorithm = algorithm
+        return self
+
     def build(self, ctx: Context | None = None) -> FastIca:
-        return FastIca(self._rng, fun=self._fun, ctx=ctx)
+        return FastIca(self._rng, fun=self._fun, ctx=ctx, algorithm=self._algorithm)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -734,6 +763,22 @@ def ica_par(x1t: np.ndarray, tol: float, max_iter: int, w_init: np.ndarray, fun:
     fn = getattr(ctx.lib, f"petal_ica_par_{_SUFFIX[x1t.dtype]}")
     ctx.check(fn(ctx.handle, _np_ptr(x1t), n, nc, fun, float(tol), int(max_iter), int(lim_variant), _np_ptr(w_init),
                  _np_ptr(w), C.byref(n_iter), C.byref(lim)))
+    return w, int(n_iter.value)
+
+
+def ica_def(x1t: np.ndarray, tol: float, max_iter: int, w_init: np.ndarray, fun: int = LOGCOSH,
+            ctx: Context | None = None):
+    """Deflation FastICA on whitened data (sklearn `_ica_def`, _fastica.py:65-100); x1t is samples x components."""
+    ctx = _ctx_for(ctx)
+    x1t = np.asarray(x1t)
+    x1t = np.ascontiguousarray(x1t, dtype=np.float32 if x1t.dtype == np.float32 else np.float64)
+    w_init = np.ascontiguousarray(w_init, dtype=np.float64)
+    n, nc = x1t.shape
+    w = np.empty((nc, nc))
+    n_iter, lim = C.c_int64(0), C.c_double(0.0)
+    fn = getattr(ctx.lib, f"petal_ica_defl_{_SUFFIX[x1t.dtype]}")
+    ctx.check(fn(ctx.handle, _np_ptr(x1t), n, nc, fun, float(tol), int(max_iter), _np_ptr(w_init), _np_ptr(w),
+                 C.byref(n_iter), C.byref(lim)))
     return w, int(n_iter.value)
 
 

@@ -69,6 +69,16 @@ struct petal_ctx {
     // device-side status word raised by kernels that cannot report through the host (Jacobi sweeps exhausted)
     int* dev_status = nullptr;
     bool status_armed = false;  // a kernel that may raise dev_status was launched during this call
+    // host-resident X (row_stream.cuh): 0 = auto (resident copy when it fits, else out-of-core ring), 1 = always a
+    // resident copy, 2 = always the two-slot ring; rows of X per H2D chunk are derived from host_chunk_bytes
+    int host_staging = 0;
+    int64_t host_chunk_bytes = (int64_t)1 << 30;
+    cudaStream_t copy_stream = nullptr;   // created on first use
+    cudaEvent_t copy_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // ready[2], freed[2], alloc
+    // statistics of the last call that streamed a host X (petal_ctx_host_stream_stats)
+    int64_t last_h2d_bytes = 0;
+    int64_t last_traversals = 0;
+    int last_ring = 0;
 };
 
 namespace petal {

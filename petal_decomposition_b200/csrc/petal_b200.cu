@@ -7,11 +7,13 @@
 
 #include "comm.cuh"
 #include "common.cuh"
+#include "row_stream.cuh"
 #include "small_linalg.cuh"
 #include "stream_kernels.cuh"
 #include "dense_f64.cuh"
 #include "tc_kernels.cuh"
 #include "ica_kernels.cuh"
+#include "ica_deflation.cuh"
 
 using namespace petal;
 
@@ -287,8 +289,7 @@ struct ColMean {
 
 // reference: input.mean_axis(Axis(0)) (src/pca.rs:207,521; src/ica.rs:174)
 template <typename T>
-void compute_mean(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, bool centering,
-                  ColMean<T>& out) {
+void compute_mean(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, bool centering, ColMean<T>& out) {
     out.mean_d.alloc(ctx, (size_t)d);
     out.mean_t.alloc(ctx, (size_t)d);
     out.mean_d.zero();
@@ -297,7 +298,7 @@ void compute_mean(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_to
     if (!centering || d == 0) return;
     DBuf<double> sum(ctx, (size_t)d);
     sum.zero();
-    launch_colsum<T>(ctx, X, n, d, d, sum.p);
+    X.traverse([&](const T* Xc, int64_t, int64_t rows) { launch_colsum<T>(ctx, Xc, rows, d, d, sum.p); });
     allreduce_sum(ctx, sum.p, (size_t)d);
     finish_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, 1.0 / (double)n_total, d,
                                                                                out.mean_d.p, out.mean_t.p);
@@ -305,27 +306,95 @@ void compute_mean(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_to
     out.mu = out.mean_t.p;
 }
 
-// G[d x d] (f64) = (X - mu)^T (X - mu), all-reduced over ranks and mirrored.
+// G[d x d] (f64) += (X - mu)^T (X - mu) over `n` rows (this rank's partial; upper tiles only on the symmetric engines)
 template <typename T>
-void centered_gram(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G) {
-    PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
-    bool done = false;
+void centered_gram_acc(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G) {
     if constexpr (sizeof(T) == 4) {
         // narrow f32 Gram (d <= 128): one tcgen05 pass, both operands centred on load
         if (ctx->f32_engine == 1 && tc::atb_supported(X, ld, d, X, ld, d, n) && is_aligned16(mu)) {
             tc::launch_tc_atb(ctx, X, ld, d, mu, X, ld, d, n, G, d, false, nullptr, mu);
-            done = true;
+            return;
         }
     }
-    if (!done) {
-        AtbParams<T> p{};
-        p.A = X; p.lda = ld; p.da = d; p.mua = mu;
-        p.B = X; p.ldb = ld; p.db = d; p.mub = mu;
-        p.n = n; p.C = G; p.ldc = d; p.symmetric = 1;
-        launch_atb<T>(ctx, p);
-    }
+    AtbParams<T> p{};
+    p.A = X; p.lda = ld; p.da = d; p.mua = mu;
+    p.B = X; p.ldb = ld; p.db = d; p.mub = mu;
+    p.n = n; p.C = G; p.ldc = d; p.symmetric = 1;
+    launch_atb<T>(ctx, p);
+}
+// G[d x d] (f64) = (X - mu)^T (X - mu), all-reduced over ranks and mirrored.
+template <typename T>
+void centered_gram(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G) {
+    PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
+    centered_gram_acc<T>(ctx, X, n, d, ld, mu, G);
     allreduce_sum(ctx, G, (size_t)(d * d));
     launch_symmetrize(ctx, G, d);
+}
+
+// Column means and centred Gram matrix of a row stream (exact PCA pass 1, FastICA whitening).
+//  X in HBM: the two passes of the reference order (mean, then the Gram of the centred rows).
+//  X on the host: ONE traversal (one trip over PCIe, and the Gram runs underneath the transfer): the rows are
+//  centred with a provisional mean mu~ (first rows of every rank's shard, all-reduced), the same traversal takes the
+//  column sums c = sum(x - mu~), and with delta = mu - mu~ (mu = the type-T mean the later passes subtract)
+//      (X - mu)^T (X - mu) = G~ - c delta^T - delta c^T + n delta delta^T.
+//  delta is of the order sigma / sqrt(sample), so nothing cancels.
+__global__ void gram_shift_kernel(double* __restrict__ G, int64_t d, const double* __restrict__ c,
+                                  const double* __restrict__ delta, double n_total) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d * d) return;
+    const int64_t i = idx / d, j = idx % d;
+    G[idx] += -c[i] * delta[j] - delta[i] * c[j] + n_total * delta[i] * delta[j];
+}
+// sum[j] (column sums of x over all ranks) -> mean (type T and its f64 image), c = sum - n mu~, delta = mu - mu~
+template <typename T>
+__global__ void shifted_mean_kernel(const double* __restrict__ sum, const double* __restrict__ mu0, double n_total, int64_t d,
+                                    double* __restrict__ mean_d, T* __restrict__ mean_t, double* __restrict__ c,
+                                    double* __restrict__ delta) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d) return;
+    const T mt = (T)(sum[j] / n_total);
+    c[j] = sum[j] - n_total * mu0[j];
+    delta[j] = (double)mt - mu0[j];
+    mean_t[j] = mt;
+    mean_d[j] = (double)mt;
+}
+template <typename T>
+void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, bool centering, ColMean<T>& cm, double* G) {
+    const bool one_trip = X.host && !X.loaded;  // rank-uniform by construction only on a single rank; see below
+    if (!one_trip || ctx->world > 1 || !centering) {
+        // (several ranks: the provisional mean would need its own collective; the plain order keeps the collectives of
+        //  host-fed and device-fed ranks identical)
+        compute_mean<T>(ctx, X, d, n_total, centering, cm);
+        PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
+        X.traverse([&](const T* Xc, int64_t, int64_t rows) { centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mu, G); });
+        allreduce_sum(ctx, G, (size_t)(d * d));
+        launch_symmetrize(ctx, G, d);
+        return;
+    }
+    cm.mean_d.alloc(ctx, (size_t)d);
+    cm.mean_t.alloc(ctx, (size_t)d);
+    DBuf<double> sum(ctx, (size_t)d + 1), mu0(ctx, (size_t)d), c(ctx, (size_t)d), delta(ctx, (size_t)d);
+    DBuf<T> head_tmp;
+    sum.zero();
+    const int64_t rows_s = std::min<int64_t>(X.n, 8192);
+    launch_colsum<T>(ctx, X.head(rows_s, head_tmp), rows_s, d, d, sum.p);
+    set_value_kernel<<<1, 1, 0, ctx->stream>>>(sum.p + d, (double)rows_s);
+    launch1(ctx);
+    provisional_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, d, mu0.p, cm.mean_t.p);
+    launch1(ctx);
+    sum.zero();
+    PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
+    X.traverse([&](const T* Xc, int64_t, int64_t rows) {
+        launch_colsum<T>(ctx, Xc, rows, d, d, sum.p);
+        centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mean_t.p, G);
+    });
+    launch_symmetrize(ctx, G, d);
+    shifted_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, mu0.p, (double)n_total, d, cm.mean_d.p,
+                                                                               cm.mean_t.p, c.p, delta.p);
+    launch1(ctx);
+    gram_shift_kernel<<<(unsigned)ceil_div(d * d, 256), 256, 0, ctx->stream>>>(G, d, c.p, delta.p, (double)n_total);
+    launch1(ctx);
+    cm.mu = cm.mean_t.p;
 }
 
 template <typename T>
@@ -374,11 +443,11 @@ void gemm_xb_b64(petal_ctx* ctx, const T* A, int64_t lda, int64_t n, int64_t K, 
     gemm_xb<T>(ctx, A, lda, n, K, Bt.p, ldb, false, L, mu, nullptr, Y, ldy);
 }
 
-// C[da x db] (f64, zeroed here) = (A - mua)^T (B - mub)
+// C[da x db] (f64, zeroed here unless !zero: then accumulated) = (A - mua)^T (B - mub)
 template <typename T>
 void gemm_atb(petal_ctx* ctx, const T* A, int64_t lda, int64_t da, const T* mua, const T* B, int64_t ldb,
-              int64_t db, const T* mub, int64_t n, double* C) {
-    PETAL_CUDA(cudaMemsetAsync(C, 0, (size_t)(da * db) * sizeof(double), ctx->stream));
+              int64_t db, const T* mub, int64_t n, double* C, bool zero = true) {
+    if (zero) PETAL_CUDA(cudaMemsetAsync(C, 0, (size_t)(da * db) * sizeof(double), ctx->stream));
     if constexpr (sizeof(T) == 4) {
         if (ctx->f32_engine == 1 && mub == nullptr && tc::atb_supported(A, lda, da, B, ldb, db, n) &&
             is_aligned16(mua)) {
@@ -483,12 +552,12 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
     if (n_total == 0) return;                                  // src/pca.rs:207-211
     if (d == 0) return;
 
-    DevIn<T> X(ctx, x_user, (size_t)(n * d));
+    RowStream<T> X;
+    X.open(ctx, x_user, n, d, (size_t)(10 * d * d) * sizeof(double) + ((size_t)1 << 30) + (size_t)(n * k) * sizeof(T));
     DevOut<T> comps(ctx, comps_u, (size_t)(k * d)), mean(ctx, mean_u, (size_t)d), sing(ctx, sing_u, (size_t)k),
         tv(ctx, tv_u, 1), scores(ctx, scores_u, (size_t)(n * k));
 
     ColMean<T> cm;
-    compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
 
     // sigma and Vt of the centred data (what the reference takes from gesvd, src/pca.rs:216-220); the n x n U is
     // never formed.
@@ -499,7 +568,7 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
     //       below 1e-12 of the largest diagonal entry, or fewer rows than columns) takes the second route.
     //  f32, and the fallback: eigen-decomposition of G1 (f64 accumulation: far inside the f32 tolerance).
     DBuf<double> G(ctx, (size_t)(d * d)), Jt(ctx, (size_t)(d * d)), lam(ctx, (size_t)d), tvd(ctx, 1);
-    centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
+    mean_and_gram<T>(ctx, X, d, n_total, centering, cm, G.p);
     trace_kernel<<<1, 256, 0, ctx->stream>>>(G.p, d, tvd.p);  // sum of all sigma^2, src/pca.rs:224
     launch1(ctx);
     bool have_sigma = false;  // lam holds sigma (true) or sigma^2 (false)
@@ -523,15 +592,17 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
                 int64_t rows_c = std::max<int64_t>(128, ((int64_t)1 << 30) / (d * (int64_t)sizeof(double)));
                 rows_c = std::min<int64_t>(std::max<int64_t>(n, 1), (rows_c / 128) * 128);
                 DBuf<double> Q1(ctx, (size_t)(rows_c * d));
-                for (int64_t r0 = 0; r0 < n; r0 += rows_c) {
-                    const int64_t rows = std::min<int64_t>(rows_c, n - r0);
-                    gemm_nn(ctx, reinterpret_cast<const double*>(X.p) + r0 * d, d, P1.p, d, Q1.p, d, rows, d, d, 1.0, false, false,
-                            /*b_upper=*/true, false, reinterpret_cast<const double*>(cm.mu));
-                    AtbParams<double> ap{};
-                    ap.A = Q1.p; ap.lda = d; ap.da = d; ap.B = Q1.p; ap.ldb = d; ap.db = d; ap.n = rows; ap.C = G2.p; ap.ldc = d;
-                    ap.symmetric = 1;
-                    launch_atb<double>(ctx, ap);
-                }
+                X.traverse([&](const T* Xc, int64_t, int64_t rows_x) {
+                    for (int64_t r0 = 0; r0 < rows_x; r0 += rows_c) {
+                        const int64_t rows = std::min<int64_t>(rows_c, rows_x - r0);
+                        gemm_nn(ctx, reinterpret_cast<const double*>(Xc) + r0 * d, d, P1.p, d, Q1.p, d, rows, d, d, 1.0, false, false,
+                                /*b_upper=*/true, false, reinterpret_cast<const double*>(cm.mu));
+                        AtbParams<double> ap{};
+                        ap.A = Q1.p; ap.lda = d; ap.da = d; ap.B = Q1.p; ap.ldb = d; ap.db = d; ap.n = rows; ap.C = G2.p; ap.ldc = d;
+                        ap.symmetric = 1;
+                        launch_atb<double>(ctx, ap);
+                    }
+                });
                 allreduce_sum(ctx, G2.p, (size_t)(d * d));
                 launch_symmetrize(ctx, G2.p, d);
                 DBuf<double> P2(ctx, (size_t)(d * d));
@@ -569,7 +640,9 @@ void pca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, b
             scores_tmp.alloc(ctx, (size_t)(n * k));
             scores_dev = scores_tmp.p;
         }
-        gemm_xb<T>(ctx, X.p, d, n, d, comps_dev, d, true, k, cm.mu, nullptr, scores_dev, k);
+        X.traverse([&](const T* Xc, int64_t r0, int64_t rows) {
+            gemm_xb<T>(ctx, Xc, d, rows, d, comps_dev, d, true, k, cm.mu, nullptr, scores_dev + r0 * k, k);
+        });
         flip_signs<T>(ctx, scores_dev, n, k, comps_dev, d, (bool)scores);
         if (sing) {
             if (have_sigma) {
@@ -616,10 +689,23 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     if (l == 0) return;
 
     PhaseClock pc(ctx);
-    DevIn<T> X(ctx, x_user, (size_t)(n * d));
+    const int64_t ly = ((l + 15) / 16) * 16;  // row pitch of Y: whole 64 B chunks (TMA reads, vector epilogue stores)
+    RowStream<T> X;
+    X.open(ctx, x_user, n, d, (size_t)(2 * n * ly + n * k) * sizeof(T) + (size_t)(8 * d * l) * sizeof(double));
     DevIn<T> Omega(ctx, omega_user, (size_t)(d * l_full));
     DevOut<T> comps(ctx, comps_u, (size_t)(k * d)), mean(ctx, mean_u, (size_t)d), sing(ctx, sing_u, (size_t)k),
         tv(ctx, tv_u, 1), scores(ctx, scores_u, (size_t)(n * k));
+
+    // f32 on the tcgen05 engine keeps Y panel-major ([row block of 32][ly][32]): tc_xb then writes whole 128 B
+    // lines and tc_atb reads its B tiles by TMA without transposing (see tc_kernels.cuh).
+    // rank-uniform: every rank can run the panel path on every chunk of its shard (otherwise ranks would issue
+    // different collectives: the panel path reduces C' = Xc^T Y, the row-major path G1, then [G2 | C'])
+    bool panel = false;
+    if constexpr (sizeof(T) == 4) {
+        panel = ginfo.cap[0] && X.chunks_aligned16() && tc::xb_supported(nullptr, d, X.min_chunk_rows(), d, l) &&
+                X.min_chunk_rows() >= 1024;
+        if (ginfo.cap[0] && !panel && ctx->world > 1) linalg_error("inconsistent panel-path decision across ranks");
+    }
 
     // Column means.  On the panel path (f32, tcgen05) with at least one power iteration and a spare padding column
     // in the Y panel, the separate pass over X is saved: X Omega runs with a provisional mean mu~ taken from a row
@@ -629,17 +715,17 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     ColMean<T> cm;
     bool fold_mean = false;
     if constexpr (sizeof(T) == 4) {
-        const int64_t l_ = std::min<int64_t>(l_full, std::min<int64_t>(n_total, d));
-        fold_mean = ginfo.cap[0] && centering && n_iter >= 1 && (l_ % 16) != 0;
+        fold_mean = panel && centering && n_iter >= 1 && (l % 16) != 0;
         if (const char* e = getenv("PETAL_FOLD_MEAN")) fold_mean = fold_mean && atoi(e) != 0;
     }
     if (fold_mean) {
         cm.mean_d.alloc(ctx, (size_t)d);
         cm.mean_t.alloc(ctx, (size_t)d);
         DBuf<double> sum(ctx, (size_t)d + 1);
+        DBuf<T> head_tmp;
         sum.zero();
         const int64_t rows_s = std::min<int64_t>(n, 8192);
-        launch_colsum<T>(ctx, X.p, rows_s, d, d, sum.p);
+        launch_colsum<T>(ctx, X.head(rows_s, head_tmp), rows_s, d, d, sum.p);
         set_value_kernel<<<1, 1, 0, ctx->stream>>>(sum.p + d, (double)rows_s);
         launch1(ctx);
         allreduce_sum(ctx, sum.p, (size_t)d + 1);
@@ -647,22 +733,11 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         launch1(ctx);
         cm.mu = cm.mean_t.p;
     } else {
-        compute_mean<T>(ctx, X.p, n, d, n_total, centering, cm);
+        compute_mean<T>(ctx, X, d, n_total, centering, cm);
     }
     const double cutoff = rank_cutoff<T>();
     pc.mark("stage inputs + mean");
 
-    // Y = Xc * Omega (src/pca.rs:707), fused with ||Xc||_F^2 (src/pca.rs:533)
-    const int64_t ly = ((l + 15) / 16) * 16;  // row pitch of Y: whole 64 B chunks (TMA reads, vector epilogue stores)
-    // f32 on the tcgen05 engine keeps Y panel-major ([row block of 32][ly][32]): tc_xb then writes whole 128 B
-    // lines and tc_atb reads its B tiles by TMA without transposing (see tc_kernels.cuh)
-    bool panel = false;
-    if constexpr (sizeof(T) == 4) {
-        // rank-uniform: every rank can run the panel path on its shard (otherwise ranks would issue different
-        // collectives: the panel path reduces C' = Xc^T Y, the row-major path G1, then [G2 | C'])
-        panel = ginfo.cap[0] && tc::xb_supported(X.p, d, n, d, l) && is_aligned16(cm.mu);
-        if (ginfo.cap[0] && !panel && ctx->world > 1) linalg_error("inconsistent panel-path decision across ranks");
-    }
     const int64_t nblk = ceil_div(n, 32);
     DBuf<T> Y(ctx, panel ? (size_t)(nblk * ly * 32) : (size_t)(n * ly));
     // y - tf32(y), the B_lo operand of the X^T Y passes, is derived inside tc_atb by default; PETAL_YLO=1 keeps the
@@ -676,80 +751,86 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     DBuf<double> P(ctx, (size_t)(l * l));
     DBuf<T> Y1;
     PETAL_CUDA(cudaMemsetAsync(tvd, 0, sizeof(double), ctx->stream));
-    if constexpr (sizeof(T) == 4) {
-        // Only the passes that define the result (the last Y and C' = Xc^T Y) run with cut accumulation chains;
-        // the power iterations in between only have to keep the dominant subspace and use the faster long chains.
-        if (panel)
-            tc::launch_tc_xb<float>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, Y.p, ly, tvd, true, Ylo.p,
-                                    n_iter == 0 ? -1 : 0, nullptr, -1, fold_mean ? (int)l : -1);
-    }
-    if (fold_mean && !panel) linalg_error("inconsistent panel-path decision (folded mean)");
-    if (!panel) gemm_xb<T>(ctx, X.p, d, n, d, Omega.p, l_full, false, l, cm.mu, nullptr, Y.p, ly, tvd);
 
-    pc.mark("Y = Xc Omega");
-    // power iterations (src/pca.rs:708-715): Z = Xc^T Y, re-orthonormalise, Y = Xc Z
-    DBuf<double> Zd(ctx, (size_t)(d * l));
-    auto xty_pass = [&](double* out, int precise) {  // out[d x l] = Xc^T Y
-        if constexpr (sizeof(T) == 4) {
-            if (panel) {
-                PETAL_CUDA(cudaMemsetAsync(out, 0, (size_t)(d * l) * sizeof(double), ctx->stream));
-                tc::launch_tc_atb(ctx, X.p, d, d, cm.mu, Y.p, ly, l, n, out, l, true, Ylo.p, nullptr, precise);
-                return;
-            }
-        }
-        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y.p, ly, l, nullptr, n, out);
-    };
-    // X^T Y: its truncation bias (unlike X Z's, which mostly rescales columns) tilts the subspace, and what the
-    // measured: even two long-chain passes at the start cost two digits on the trailing components, so all of them
-    // run with cut chains (PETAL_ATB_FAST_ITERS = number of leading iterations on the fast path, for experiments)
+    // The range finder (src/pca.rs:707-715) as q + 1 traversals of X.  Traversal j computes, chunk by chunk,
+    //     Y_c = Xc_c B_j     (B_0 = Omega: src/pca.rs:707, fused with ||Xc||_F^2, src/pca.rs:533; B_j = orth(Z_j): :713)
+    //     Z_{j+1} += Xc_c^T Y_c   (src/pca.rs:711; the last one is C' = Xc^T Y of the projection, src/pca.rs:681)
+    // Both contractions of an iteration only need the chunk that is resident, so a host X that does not fit in HBM
+    // crosses PCIe q + 1 times instead of 2q + 2, and a host X that does fit is consumed while it arrives.
+    // With X in HBM there is one chunk and this is the plain pass order.
+    // Only the passes that define the result (the last Y and C' = Xc^T Y) run with cut accumulation chains; the
+    // X Z passes of the power iterations in between only have to keep the dominant subspace and use the faster long
+    // chains.  X^T Y: its truncation bias (unlike X Z's, which mostly rescales columns) tilts the subspace - measured:
+    // even two long-chain passes at the start cost two digits on the trailing components, so all of them run with cut
+    // chains (PETAL_ATB_FAST_ITERS = number of leading iterations on the fast path, for experiments).
     int64_t fast_atb_iters = 0;
     if (const char* e = getenv("PETAL_ATB_FAST_ITERS")) fast_atb_iters = atoi(e);
-    for (int64_t it = 0; it < n_iter; ++it) {
-        bool folded = false;
-        if constexpr (sizeof(T) == 4) {
-            if (fold_mean && it == 0) {
-                // Zt [d x (l + 1)] = (X - mu~)^T [Y~ | 1], then the rank-one corrections
-                DBuf<double> Zt(ctx, (size_t)(d * (l + 1))), wu(ctx, (size_t)(2 * l)), sc(ctx, 2);
-                Zt.zero();
-                tc::launch_tc_atb(ctx, X.p, d, d, cm.mu, Y.p, ly, l + 1, n, Zt.p, l + 1, true, Ylo.p, nullptr,
-                                  it < fast_atb_iters ? 0 : -1);
-                allreduce_sum(ctx, Zt.p, (size_t)(d * (l + 1)));
+    DBuf<double> Zd(ctx, (size_t)(d * l)), Zacc(ctx, (size_t)(d * (l + 1))), wu(ctx, (size_t)(2 * l)), sc(ctx, 2);
+    if (fold_mean && !panel) linalg_error("inconsistent panel-path decision (folded mean)");
+    for (int64_t j = 0; j <= n_iter; ++j) {
+        const bool last = (j == n_iter);
+        const bool folded = fold_mean && j == 0;
+        // accumulator of this traversal's X^T Y: Zt [d x (l + 1)] with the ones column when the mean is folded in,
+        // C' for the last one, otherwise the next Z (never the buffer the X B products of the same traversal read)
+        const bool do_atb = panel || !last;
+        double* acc = last ? Cp : Zacc.p;
+        const int64_t acc_cols = folded ? l + 1 : l;
+        if (do_atb) PETAL_CUDA(cudaMemsetAsync(acc, 0, (size_t)(d * acc_cols) * sizeof(double), ctx->stream));
+        const int xb_precise = last ? -1 : 0;
+        const int atb_precise = (!last && j < fast_atb_iters) ? 0 : -1;
+        X.traverse([&](const T* Xc, int64_t r0, int64_t rows) {
+            bool done = false;
+            if constexpr (sizeof(T) == 4) {
+                if (panel) {
+                    float* Yc = Y.p + (r0 / 32) * ly * 32;
+                    float* Yloc = ylo_panel ? Ylo.p + (r0 / 32) * ly * 32 : nullptr;
+                    if (j == 0)
+                        tc::launch_tc_xb<float>(ctx, Xc, d, rows, d, Omega.p, l_full, false, l, cm.mu, Yc, ly, tvd, true, Yloc,
+                                                xb_precise, nullptr, -1, fold_mean ? (int)l : -1);
+                    else
+                        tc::launch_tc_xb<double>(ctx, Xc, d, rows, d, Zd.p, l, false, l, cm.mu, Yc, ly, nullptr, true, Yloc,
+                                                 xb_precise);
+                    tc::launch_tc_atb(ctx, Xc, d, d, cm.mu, Yc, ly, acc_cols, rows, acc, acc_cols, true, Yloc, nullptr,
+                                      atb_precise);
+                    done = true;
+                }
+            }
+            if (!done) {
+                T* Yc = Y.p + r0 * ly;
+                if (j == 0) gemm_xb<T>(ctx, Xc, d, rows, d, Omega.p, l_full, false, l, cm.mu, nullptr, Yc, ly, tvd);
+                else gemm_xb_b64<T>(ctx, Xc, d, rows, d, Zd.p, l, l, cm.mu, Yc, ly);
+                if (do_atb) gemm_atb<T>(ctx, Xc, d, d, cm.mu, Yc, ly, l, nullptr, rows, acc, /*zero=*/false);
+            }
+        });
+        pc.mark(last ? "Y = Xc Z, C' = Xc^T Y" : "  Y = Xc B, Z = Xc^T Y");
+        if (last) break;
+        if (folded) {
+            if constexpr (sizeof(T) == 4) {
+                // Zt = (X - mu~)^T [Y~ | 1], then the rank-one corrections
+                allreduce_sum(ctx, Zacc.p, (size_t)(d * (l + 1)));
                 const double inv_n = 1.0 / (double)n_total;
-                fold_mean_vectors_kernel<T><<<(unsigned)(l + 1), 256, 0, ctx->stream>>>(Zt.p, Omega.p, l_full, d, l, inv_n,
+                fold_mean_vectors_kernel<T><<<(unsigned)(l + 1), 256, 0, ctx->stream>>>(Zacc.p, Omega.p, l_full, d, l, inv_n,
                                                                                        cm.mean_d.p, wu.p, sc.p);
                 launch1(ctx);
                 fold_mean_fix_kernel<T><<<(unsigned)ceil_div(d * l, 256), 256, 0, ctx->stream>>>(
-                    Zt.p, d, l, inv_n, (double)n_total, wu.p, sc.p, cm.mean_d.p, 1.0 / (double)ctx->world, Zd.p, tvd);
+                    Zacc.p, d, l, inv_n, (double)n_total, wu.p, sc.p, cm.mean_d.p, 1.0 / (double)ctx->world, Zd.p, tvd);
                 launch1(ctx);
-                fold_mean_commit_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(Zt.p, d, l, inv_n, cm.mean_d.p,
+                fold_mean_commit_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(Zacc.p, d, l, inv_n, cm.mean_d.p,
                                                                                              cm.mean_t.p);
                 launch1(ctx);
-                folded = true;
             }
+        } else {
+            allreduce_sum(ctx, Zacc.p, (size_t)(d * l));
+            PETAL_CUDA(cudaMemcpyAsync(Zd.p, Zacc.p, (size_t)(d * l) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         }
-        if (!folded) {
-            xty_pass(Zd.p, it < fast_atb_iters ? 0 : -1);
-            allreduce_sum(ctx, Zd.p, (size_t)(d * l));
-        }
-        pc.mark("  Z = Xc^T Y");
         orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
         pc.mark("  orth(Z)");
-        bool done = false;
-        if constexpr (sizeof(T) == 4) {
-            if (panel) {
-                tc::launch_tc_xb<double>(ctx, X.p, d, n, d, Zd.p, l, false, l, cm.mu, Y.p, ly, nullptr, true, Ylo.p,
-                                         it == n_iter - 1 ? -1 : 0);
-                done = true;
-            }
-        }
-        if (!done) gemm_xb_b64<T>(ctx, X.p, d, n, d, Zd.p, l, l, cm.mu, Y.p, ly);
-        pc.mark("  Y = Xc Z");
     }
 
     if (panel) {
         // thin QR of Y (src/pca.rs:716), implicit: G = Y^T Y accumulated in f64 from the exact fp32 products,
         // P = R^-1 (Cholesky; Jacobi when rank deficient) so that Q = Y P is orthonormal to eps64 * cond(Y)^2.
-        // B = Q^T Xc (src/pca.rs:681) = P^T (Y^T Xc): C' = Xc^T Y in one pass over X.
+        // B = Q^T Xc (src/pca.rs:681) = P^T (Y^T Xc): C' = Xc^T Y came out of the last traversal.
         // After a power iteration Y = Xc Z with the replicated Z still in Zd, so G = Y^T Y = Z^T (Xc^T Y) = Z^T C':
         // a small replicated product instead of another pass over Y (same ~eps32 relative accuracy as the
         // fp32-accumulated pass over the panels it replaces; that pass remains for n_iter == 0).
@@ -766,7 +847,6 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
                                              (size_t)l * sizeof(double), (size_t)l, cudaMemcpyDeviceToDevice, ctx->stream));
             }
         }
-        xty_pass(Cp, -1);
         if (gram_from_c) {
             allreduce_sum(ctx, Cp, (size_t)(d * l + 1));
             gemm_atb<double>(ctx, Zd.p, l, l, nullptr, Cp, l, l, nullptr, d, G2);
@@ -774,7 +854,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         } else {
             allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
         }
-        pc.mark("G = Y^T Y, C' = Xc^T Y");
+        pc.mark("G = Y^T Y");
         gram_to_orthonormalizer(ctx, G2, l, cutoff, kGramNoise, P.p);
     } else {
         // thin QR of Y (src/pca.rs:716) done implicitly in two Gram rounds (CholeskyQR2-style, with a
@@ -790,7 +870,10 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         pc.mark("Y1 = Y P1");
         // B = Q^T Xc (src/pca.rs:681) = P2^T (Y1^T Xc):  C' = Xc^T Y1 (d x l) in one pass over X
         gemm_atb<T>(ctx, Y1.p, ly, l, nullptr, Y1.p, ly, l, nullptr, n, G2);
-        gemm_atb<T>(ctx, X.p, d, d, cm.mu, Y1.p, ly, l, nullptr, n, Cp);
+        PETAL_CUDA(cudaMemsetAsync(Cp, 0, (size_t)(d * l) * sizeof(double), ctx->stream));
+        X.traverse([&](const T* Xc, int64_t r0, int64_t rows) {
+            gemm_atb<T>(ctx, Xc, d, d, cm.mu, Y1.p + r0 * ly, ly, l, nullptr, rows, Cp, /*zero=*/false);
+        });
         allreduce_sum(ctx, small.p, (size_t)(l * l + d * l + 1));
         pc.mark("G2, C' = Xc^T Y1");
         gram_to_orthonormalizer(ctx, G2, l, 1e-6, kGramNoise, P.p);  // P2 (l x l)
@@ -880,10 +963,14 @@ void transform(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, const T* c
                const T* mean_user, T* out_user) {
     if (n < 0 || d < 0 || k < 0) invalid_input("negative dimension");
     if (n == 0 || k == 0) return;
-    DevIn<T> X(ctx, x_user, (size_t)(n * d)), C(ctx, comps_user, (size_t)(k * d)), mu(ctx, mean_user, (size_t)d);
+    RowStream<T> X;
+    X.open(ctx, x_user, n, d, (size_t)(n * k) * sizeof(T));
+    DevIn<T> C(ctx, comps_user, (size_t)(k * d)), mu(ctx, mean_user, (size_t)d);
     DevOut<T> out(ctx, out_user, (size_t)(n * k));
     if (!out) invalid_input("output buffer is null");
-    gemm_xb<T>(ctx, X.p, d, n, d, C.p, d, true, k, mu.p, nullptr, out.p, k);
+    X.traverse([&](const T* Xc, int64_t r0, int64_t rows) {
+        gemm_xb<T>(ctx, Xc, d, rows, d, C.p, d, true, k, mu.p, nullptr, out.p + r0 * k, k);
+    });
     out.commit(ctx);
     finish_call(ctx, out.to_host);
 }
@@ -894,8 +981,37 @@ void inverse_transform(petal_ctx* ctx, const T* y_user, int64_t n, int64_t k, co
     if (n < 0 || d < 0 || k < 0) invalid_input("negative dimension");
     if (n == 0 || d == 0) return;
     DevIn<T> Y(ctx, y_user, (size_t)(n * k)), C(ctx, comps_user, (size_t)(k * d)), mu(ctx, mean_user, (size_t)d);
+    if (out_user == nullptr) invalid_input("output buffer is null");
+    // host output (n x d, the large side here): computed in row chunks into a two-slot device buffer and drained by the
+    // copy stream while the next chunk is computed - the reconstruction never has to fit in HBM
+    int64_t rows_each = std::max<int64_t>(kMinChunkRows, ctx->host_chunk_bytes / std::max<int64_t>(d * (int64_t)sizeof(T), 1));
+    if (const char* e = getenv("PETAL_HOST_CHUNK_BYTES")) rows_each = std::max<int64_t>(kMinChunkRows, atoll(e) / (d * (int64_t)sizeof(T)));
+    rows_each = (rows_each / 32) * 32;
+    if (!is_device_pointer(out_user) && n > rows_each + kMinChunkRows) {
+        ensure_copy_stream(ctx);
+        DBuf<T> slots(ctx, (size_t)(2 * (rows_each + kMinChunkRows) * d));
+        bool used[2] = {false, false};
+        int64_t r0 = 0;
+        for (int64_t c = 0; r0 < n; ++c) {
+            int64_t rows = std::min<int64_t>(rows_each, n - r0);
+            if (n - (r0 + rows) < kMinChunkRows) rows = n - r0;
+            const int slot = (int)(c & 1);
+            T* dst = slots.p + (size_t)slot * (size_t)((rows_each + kMinChunkRows) * d);
+            if (used[slot]) PETAL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[2 + slot], 0));  // slot drained
+            gemm_xb<T>(ctx, Y.p + r0 * k, k, rows, k, C.p, d, false, d, nullptr, mu.p, dst, d);
+            PETAL_CUDA(cudaEventRecord(ctx->copy_ev[slot], ctx->stream));
+            PETAL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[slot], 0));
+            PETAL_CUDA(cudaMemcpyAsync(out_user + (size_t)r0 * (size_t)d, dst, (size_t)(rows * d) * sizeof(T), cudaMemcpyDeviceToHost,
+                                       ctx->copy_stream));
+            PETAL_CUDA(cudaEventRecord(ctx->copy_ev[2 + slot], ctx->copy_stream));
+            used[slot] = true;
+            r0 += rows;
+        }
+        PETAL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+        return;
+    }
     DevOut<T> out(ctx, out_user, (size_t)(n * d));
-    if (!out) invalid_input("output buffer is null");
     gemm_xb<T>(ctx, Y.p, k, n, k, C.p, d, false, d, nullptr, mu.p, out.p, d);
     out.commit(ctx);
     finish_call(ctx, out.to_host);
@@ -1231,18 +1347,24 @@ struct IcaOnePass<float> {
 // the whitened sample is x1 = K1 (x - mu) with K1 = sqrt(n) K (nc x d); K1 == nullptr means the
 // data is already white (d == nc).  Returns W (nc x nc, f64, device) and the iteration count.
 template <typename T>
-void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, const T* mu, const double* K1,
+void ica_par(petal_ctx* ctx, RowStream<T>& Xs, int64_t d, int64_t n_total, const T* mu, const double* K1,
              int64_t nc, int fun, double tol, int64_t max_iter, int lim_variant, const double* w_init, double* W,
              int64_t* n_iter_out, double* lim_out, bool one_pass_all_ranks = true) {
+    const int64_t n = Xs.n;
+    Xs.load();  // a host X that fits becomes resident here (the fit flow has already loaded it with its first pass)
+    // out-of-core X (ring): every fixed-point iteration re-streams the rows through the generic three-kernel pass,
+    // chunk by chunk (PCIe-bound; the one-pass kernel addresses all of X through one tensor map)
+    const T* X = Xs.ring ? nullptr : Xs.resident_ptr();
     if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
     DBuf<double> Wk(ctx, (size_t)(nc * d)), Hg(ctx, (size_t)(nc * d)), Htg(ctx, (size_t)(nc * d + nc)), HK(ctx, (size_t)(nc * nc)),
         Gd(ctx, (size_t)(nc * nc)), W1(ctx, (size_t)(nc * nc)), limd(ctx, 1);
     // the one-pass kernel changes how often the host polls (and with it the number of collectives per batch):
     // taken only when every rank can run it on its shard
-    const bool one_pass = one_pass_all_ranks && ica_one_pass_supported<T>(ctx, X, d, n, d, nc);
+    const bool one_pass = one_pass_all_ranks && !Xs.ring && ica_one_pass_supported<T>(ctx, X, d, n, d, nc);
     if (one_pass_all_ranks && !one_pass && ctx->world > 1 && ica_one_pass_supported<T>(ctx, nullptr, d, n, d, nc))
         linalg_error("inconsistent one-pass decision across ranks");
-    DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, one_pass ? (size_t)1 : (size_t)(n * nc));
+    const int64_t u_rows = Xs.ring ? Xs.slot_rows : n;
+    DBuf<T> Wt(ctx, (size_t)(nc * d)), U(ctx, one_pass ? (size_t)1 : (size_t)(u_rows * nc));
     double* H = Hg.p;
     const int htg_n = (int)(nc * d + nc);
     // Htg = this rank's partial [H^T (d x nc) | sum g' (nc)]; with several ranks the sum over ranks goes to a second
@@ -1306,14 +1428,16 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
             // U, g(U), sum g'(U) and H^T in a single pass over X (tcgen05; U and g(U) never reach HBM)
             pass.run(ctx);
         } else {
-            // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
-            gemm_xb<T>(ctx, X, d, n, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
-            // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
-            PETAL_CUDA(cudaMemsetAsync(gp_loc, 0, (size_t)nc * sizeof(double), ctx->stream));
-            launch_nonlin<T>(ctx, U.p, n, nc, nc, fun, gp_loc);
-            // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening],
-            // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
-            gemm_atb<T>(ctx, X, d, d, mu, U.p, nc, nc, nullptr, n, Ht_loc);
+            PETAL_CUDA(cudaMemsetAsync(Htg.p, 0, (size_t)htg_n * sizeof(double), ctx->stream));
+            Xs.traverse([&](const T* Xc, int64_t, int64_t rows) {
+                // U = (X - mu) W~^T  (n x nc)    [w.dot(input), src/ica.rs:332]
+                gemm_xb<T>(ctx, Xc, d, rows, d, Wt.p, d, true, nc, mu, nullptr, U.p, nc);
+                // g(U) in place and sum of g'(U) per component  [logcosh, src/ica.rs:383-398]
+                launch_nonlin<T>(ctx, U.p, rows, nc, nc, fun, gp_loc);
+                // H = g(U)^T (X - mu)  (nc x d)   [gwtx.dot(input.t()), src/ica.rs:333, before whitening],
+                // computed as H^T = (X - mu)^T g(U) so that the pass runs on the X^T*Y engine (tcgen05 for f32)
+                gemm_atb<T>(ctx, Xc, d, d, mu, U.p, nc, nc, nullptr, rows, Ht_loc, /*zero=*/false);
+            });
         }
         if (ctx->world > 1) allreduce_sum_to(ctx, Htg.p, Hred.p, (size_t)htg_n);
     };
@@ -1384,29 +1508,89 @@ void ica_par(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t n_total, 
     if (lim_out) *lim_out = lim;
 }
 
+// Deflation FastICA (ica_deflation.cuh; sklearn `_ica_def`) on data X[n x d] with the whitening folded in like ica_par:
+// x1 = K1 (x - mu).  Returns W (nc x nc, f64, device) and the largest iteration count over the components.
+template <typename T>
+void ica_defl(petal_ctx* ctx, RowStream<T>& Xs, int64_t d, int64_t n_total, const T* mu, const double* K1, int64_t nc,
+              int fun, double tol, int64_t max_iter, const double* w_init, double* W, int64_t* n_iter_out, double* lim_out) {
+    if (fun != PETAL_ICA_LOGCOSH && fun != PETAL_ICA_EXP && fun != PETAL_ICA_CUBE) invalid_input("unknown contrast function");
+    if (nc > 4096) invalid_input("deflation FastICA supports at most 4096 components");
+    const bool fused_pass = defl::pass_supported<T>(d);
+    DBuf<double> hacc(ctx, (size_t)d + 1), w(ctx, (size_t)nc), state(ctx, 4);
+    DBuf<T> wt(ctx, (size_t)d), U;
+    if (!fused_pass) U.alloc(ctx, (size_t)(Xs.ring ? Xs.slot_rows : Xs.n));
+    state.zero();
+    PETAL_CUDA(cudaMemsetAsync(W, 0, (size_t)(nc * nc) * sizeof(double), ctx->stream));
+    const double inv_n = 1.0 / (double)n_total;
+    const size_t upd_smem = (size_t)(2 * nc + defl::kThreads) * sizeof(double);
+    ensure_dynamic_smem(ctx, defl::defl_update_kernel<T>, upd_smem);
+    // iterations queued between two looks at the device-side state (the generic engines do not read the stop flag)
+    const int64_t batch = fused_pass ? 4 : 1;
+    double hs[4] = {0, 0, 0, 0};
+    double worst_lim = 0.0;
+    for (int64_t j = 0; j < nc; ++j) {
+        defl::defl_init_kernel<T><<<1, defl::kThreads, 0, ctx->stream>>>(w_init, (int)j, (int)nc, (int)d, K1, w.p, wt.p, state.p, hacc.p);
+        launch1(ctx);
+        int64_t it = 0;
+        while (it < max_iter) {
+            const int64_t b = std::min<int64_t>(batch, max_iter - it);
+            for (int64_t t = 0; t < b; ++t) {
+                Xs.traverse([&](const T* Xc, int64_t, int64_t rows) {
+                    if (fused_pass) {
+                        defl::launch_pass<T>(ctx, Xc, rows, d, d, mu, wt.p, fun, hacc.p, state.p);
+                    } else {
+                        // wide rows: u = (X - mu) w~ (one column), g(u) in place, h += (X - mu)^T g(u) on the generic engines
+                        gemm_xb<T>(ctx, Xc, d, rows, d, wt.p, d, true, 1, mu, nullptr, U.p, 1);
+                        launch_nonlin<T>(ctx, U.p, rows, 1, 1, fun, hacc.p + d);
+                        gemm_atb<T>(ctx, Xc, d, d, mu, U.p, 1, 1, nullptr, rows, hacc.p, /*zero=*/false);
+                    }
+                });
+                allreduce_sum(ctx, hacc.p, (size_t)d + 1);
+                {
+                    KTimer kt(ctx, "ica_defl_update", 0.0);
+                    defl::defl_update_kernel<T><<<1, defl::kThreads, upd_smem, ctx->stream>>>(hacc.p, K1, W, (int)j, (int)nc, (int)d, inv_n,
+                                                                                            tol, w.p, wt.p, state.p);
+                    launch1(ctx);
+                }
+            }
+            PETAL_CUDA(cudaMemcpyAsync(hs, state.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+            PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+            it = (int64_t)hs[1];
+            if (hs[2] != 0.0) break;
+        }
+        worst_lim = std::max(worst_lim, hs[0]);
+        defl::defl_commit_kernel<<<1, 256, 0, ctx->stream>>>(w.p, W, (int)j, (int)nc, state.p);
+        launch1(ctx);
+    }
+    PETAL_CUDA(cudaMemcpyAsync(hs, state.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->stream));
+    PETAL_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_iter_out = (int64_t)hs[3];
+    if (lim_out) *lim_out = worst_lim;
+}
+
 template <typename T>
 void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun, double tol, int64_t max_iter,
                  int lim_variant, const T* w_init_user, T* comps_u, T* mean_u, int64_t* n_iter_u, double* lim_u,
-                 T* sources_u) {
+                 T* sources_u, bool deflation = false) {
     if (n < 0 || d < 0 || max_iter < 0) invalid_input("negative dimension");
-    const bool one_pass_local = aligned_on_device(x_user) && ica_one_pass_supported<T>(ctx, nullptr, d, n, d, std::min<int64_t>(d, 64));
+    RowStream<T> X;
+    X.open(ctx, x_user, n, d, (size_t)(2 * n * std::min<int64_t>(d, n)) * sizeof(T) + (size_t)(8 * d * d) * sizeof(double));
+    const bool one_pass_local = !deflation && !X.ring && aligned_on_device(x_user) &&
+                                ica_one_pass_supported<T>(ctx, nullptr, d, n, d, std::min<int64_t>(d, 64));
     const GlobalInfo ginfo = global_info(ctx, n, one_pass_local);
     const int64_t n_total = ginfo.n_total;
     if (n_total == 0 || d == 0) return;  // src/ica.rs:174-176
     const int64_t nc = std::min<int64_t>(n_total, d);  // src/ica.rs:173
     if (w_init_user == nullptr) invalid_input("w_init (nc x nc) is required");
 
-    DevIn<T> X(ctx, x_user, (size_t)(n * d));
     DevIn<T> Winit(ctx, w_init_user, (size_t)(nc * nc));
     DevOut<T> comps(ctx, comps_u, (size_t)(nc * d)), mean(ctx, mean_u, (size_t)d), sources(ctx, sources_u, (size_t)(n * nc));
 
-    ColMean<T> cm;
-    compute_mean<T>(ctx, X.p, n, d, n_total, true, cm);
-
     // whitening (src/ica.rs:189-208): the reference takes U, sigma from gesvd of the d x n centred
     // matrix; the same U, sigma^2 are the eigenpairs of the d x d Gram Xc^T Xc.
+    ColMean<T> cm;
     DBuf<double> G(ctx, (size_t)(d * d)), Jt(ctx, (size_t)(d * d)), lam(ctx, (size_t)d);
-    centered_gram<T>(ctx, X.p, n, d, d, cm.mu, G.p);
+    mean_and_gram<T>(ctx, X, d, n_total, true, cm, G.p);
     jacobi_rows(ctx, G.p, d, d, nullptr, Jt.p, lam.p, kGramNoise);
     DBuf<double> K(ctx, (size_t)(nc * d)), K1(ctx, (size_t)(nc * d));
     const double wcut = 64.0 * 2.220446049250313e-16;  // relative eigenvalue floor of an f64-accumulated Gram matrix
@@ -1420,8 +1604,11 @@ void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun,
     launch_cast<T, double>(ctx, Winit.p, Winit_d.p, nc * nc);
     int64_t iters = 0;
     double lim = 0.0;
-    ica_par<T>(ctx, X.p, n, d, n_total, cm.mu, K1.p, nc, fun, tol, max_iter, lim_variant, Winit_d.p, Wd.p, &iters, &lim,
-               ginfo.cap[0]);
+    if (deflation)
+        ica_defl<T>(ctx, X, d, n_total, cm.mu, K1.p, nc, fun, tol, max_iter, Winit_d.p, Wd.p, &iters, &lim);
+    else
+        ica_par<T>(ctx, X, d, n_total, cm.mu, K1.p, nc, fun, tol, max_iter, lim_variant, Winit_d.p, Wd.p, &iters, &lim,
+                   ginfo.cap[0]);
 
     // components = W K (src/ica.rs:217)
     DBuf<double> Cd(ctx, (size_t)(nc * d));
@@ -1434,7 +1621,9 @@ void fastica_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int fun,
     }
     launch_cast<double, T>(ctx, Cd.p, comps_dev, nc * d);
     if (sources)  // fit_transform = (components * xc)^T (src/ica.rs:155-156)
-        gemm_xb<T>(ctx, X.p, d, n, d, comps_dev, d, true, nc, cm.mu, nullptr, sources.p, nc);
+        X.traverse([&](const T* Xc, int64_t r0, int64_t rows) {
+            gemm_xb<T>(ctx, Xc, d, rows, d, comps_dev, d, true, nc, cm.mu, nullptr, sources.p + r0 * nc, nc);
+        });
     if (mean) launch_cast<T, T>(ctx, cm.mean_t.p, mean.p, d);
     if (n_iter_u) *n_iter_u = iters;
     if (lim_u) *lim_u = lim;
@@ -1522,6 +1711,11 @@ void petal_ctx_destroy(petal_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     delete ctx->comm;
     if (ctx->dev_status) cudaFree(ctx->dev_status);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1563,6 +1757,22 @@ int petal_ctx_set_f64_engine(petal_ctx* ctx, int engine) {
     if (!ctx) return -1;
     if (engine >= 0) ctx->f64_engine = engine ? 1 : 0;
     return ctx->f64_engine;
+}
+
+int petal_ctx_set_host_staging(petal_ctx* ctx, int mode, int64_t chunk_bytes) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (mode >= 0 && mode <= 2) ctx->host_staging = mode;
+    if (chunk_bytes > 0) ctx->host_chunk_bytes = chunk_bytes;
+    return ctx->host_staging;
+}
+
+int petal_ctx_host_stream_stats(const petal_ctx* ctx, int64_t* h2d_bytes, int64_t* traversals, int* ring) {
+    if (!ctx) return PETAL_INVALID_INPUT;
+    if (h2d_bytes) *h2d_bytes = ctx->last_h2d_bytes;
+    if (traversals) *traversals = ctx->last_traversals;
+    if (ring) *ring = ctx->last_ring;
+    return PETAL_OK;
 }
 
 int petal_ctx_set_profiling(petal_ctx* ctx, int enable) {
@@ -1670,16 +1880,26 @@ int petal_comm_init(petal_ctx* ctx, const void* id, int rank, int world_size) {
                            final_lim, sources);                                                                \
         });                                                                                                    \
     }                                                                                                          \
+    int petal_fastica_deflation_fit_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, int fun,         \
+                                             double tol, int64_t max_iter, const T* w_init, T* components,     \
+                                             T* mean, int64_t* n_iter, double* final_lim, T* sources) {        \
+        return guarded(ctx, [&] {                                                                              \
+            fastica_fit<T>(ctx, x, n, d, fun, tol, max_iter, 0, w_init, components, mean, n_iter, final_lim,   \
+                           sources, /*deflation=*/true);                                                       \
+        });                                                                                                    \
+    }                                                                                                          \
     int petal_colmean_gram_##SUFFIX(petal_ctx* ctx, const T* x, int64_t n, int64_t d, int centering,            \
                                     double* mean, double* gram) {                                              \
         return guarded(ctx, [&] {                                                                              \
             const int64_t n_total = global_rows(ctx, n);                                                       \
-            DevIn<T> X(ctx, x, (size_t)(n * d));                                                               \
+            RowStream<T> X;                                                                                    \
+            X.open(ctx, x, n, d, (size_t)(4 * d * d) * sizeof(double));                                        \
             DevOut<double> m(ctx, mean, (size_t)d), g(ctx, gram, (size_t)(d * d));                             \
             if (n_total == 0 || d == 0) return;                                                                \
             ColMean<T> cm;                                                                                     \
-            compute_mean<T>(ctx, X.p, n, d, n_total, centering != 0, cm);                                      \
-            if (g) centered_gram<T>(ctx, X.p, n, d, d, cm.mu, g.p);                                            \
+            DBuf<double> gtmp;                                                                                 \
+            if (!g) gtmp.alloc(ctx, (size_t)(d * d));                                                          \
+            mean_and_gram<T>(ctx, X, d, n_total, centering != 0, cm, g ? g.p : gtmp.p);                        \
             if (m) launch_cast<double, double>(ctx, cm.mean_d.p, m.p, d);                                      \
             m.commit(ctx);                                                                                     \
             g.commit(ctx);                                                                                     \
@@ -1713,15 +1933,17 @@ PETAL_DEFINE_TYPED(f64, double)
                                int64_t* n_iter, double* final_lim) {                                              \
         return guarded(ctx, [&] {                                                                                 \
             if (n <= 0 || nc <= 0) invalid_input("empty input");                                                  \
-            const bool one_pass_local = aligned_on_device(x1t) && ica_one_pass_supported<T>(ctx, nullptr, nc, n, nc, nc); \
+            RowStream<T> X;                                                                                       \
+            X.open(ctx, x1t, n, nc, (size_t)(2 * n * nc) * sizeof(T));                                            \
+            const bool one_pass_local = !X.ring && aligned_on_device(x1t) &&                                      \
+                                        ica_one_pass_supported<T>(ctx, nullptr, nc, n, nc, nc);                   \
             const GlobalInfo gi = global_info(ctx, n, one_pass_local);                                            \
-            DevIn<T> X(ctx, x1t, (size_t)(n * nc));                                                               \
             DevIn<double> Wi(ctx, w_init, (size_t)(nc * nc));                                                     \
             DevOut<double> W(ctx, w_out, (size_t)(nc * nc));                                                      \
             if (!W) invalid_input("output buffer is null");                                                       \
             int64_t iters = 0;                                                                                    \
             double lim = 0.0;                                                                                     \
-            ica_par<T>(ctx, X.p, n, nc, gi.n_total, nullptr, nullptr, nc, fun, tol, max_iter, lim_variant, Wi.p,  \
+            ica_par<T>(ctx, X, nc, gi.n_total, nullptr, nullptr, nc, fun, tol, max_iter, lim_variant, Wi.p,       \
                        W.p, &iters, &lim, gi.cap[0]);                                                             \
             if (n_iter) *n_iter = iters;                                                                          \
             if (final_lim) *final_lim = lim;                                                                      \
@@ -1731,6 +1953,30 @@ PETAL_DEFINE_TYPED(f64, double)
     }
 PETAL_DEFINE_ICA_PAR(f32, float)
 PETAL_DEFINE_ICA_PAR(f64, double)
+
+#define PETAL_DEFINE_ICA_DEFL(SUFFIX, T)                                                                       \
+    int petal_ica_defl_##SUFFIX(petal_ctx* ctx, const T* x1t, int64_t n, int64_t nc, int fun, double tol,         \
+                                int64_t max_iter, const double* w_init, double* w_out, int64_t* n_iter,           \
+                                double* final_lim) {                                                              \
+        return guarded(ctx, [&] {                                                                                 \
+            if (n <= 0 || nc <= 0) invalid_input("empty input");                                                  \
+            RowStream<T> X;                                                                                       \
+            X.open(ctx, x1t, n, nc, (size_t)(2 * n) * sizeof(T));                                                 \
+            const int64_t n_total = global_rows(ctx, n);                                                          \
+            DevIn<double> Wi(ctx, w_init, (size_t)(nc * nc));                                                     \
+            DevOut<double> W(ctx, w_out, (size_t)(nc * nc));                                                      \
+            if (!W) invalid_input("output buffer is null");                                                       \
+            int64_t iters = 0;                                                                                    \
+            double lim = 0.0;                                                                                     \
+            ica_defl<T>(ctx, X, nc, n_total, nullptr, nullptr, nc, fun, tol, max_iter, Wi.p, W.p, &iters, &lim);  \
+            if (n_iter) *n_iter = iters;                                                                          \
+            if (final_lim) *final_lim = lim;                                                                      \
+            W.commit(ctx);                                                                                        \
+            finish_call(ctx, W.to_host);                                                                          \
+        });                                                                                                       \
+    }
+PETAL_DEFINE_ICA_DEFL(f32, float)
+PETAL_DEFINE_ICA_DEFL(f64, double)
 
 int petal_ica_nonlin_f32(petal_ctx* ctx, float* u, int64_t n, int64_t nc, int fun, int engine, double* gprime_sum) {
     return guarded(ctx, [&] { ica_nonlin<float>(ctx, u, n, nc, fun, engine, gprime_sum); });

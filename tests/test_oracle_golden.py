@@ -183,3 +183,20 @@ def test_literal_symdec_breaks_for_d3():  # SURVEY F5 (documented, not a referen
     wl = oica.symmetric_decorrelation(w, "literal")
     assert np.allclose(wt @ wt.T, np.eye(3), atol=1e-10)
     assert not np.allclose(wl @ wl.T, np.eye(3), atol=1e-3)
+
+
+# ------------------------------------------------------------------ deflation FastICA (extension)
+def test_ica_def_matches_sklearn_golden_vectors():
+    """oracle.ica.ica_def against the committed outputs of sklearn's own `_ica_def` (tests/golden/ica_deflation.json,
+    generated by tests/golden/make_ica_deflation_fixture.py): same iterates, same iteration counts."""
+    import json
+    import os
+    from oracle import ica as oica_
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ica_deflation.json")
+    fx = json.load(open(path))
+    assert fx["generator"] == "sklearn.decomposition._fastica._ica_def" and len(fx["cases"]) == 9
+    for c in fx["cases"]:
+        w, it = oica_.ica_def(np.array(c["x1"]), c["tol"], c["max_iter"], np.array(c["w_init"]), c["fun"])
+        assert it == c["n_iter"], (c["fun"], it, c["n_iter"])
+        assert np.allclose(w, np.array(c["w"]), atol=1e-13, rtol=0)
+        assert np.allclose(w @ w.T, np.eye(w.shape[0]), atol=1e-10)  # Gram-Schmidt keeps the rows orthonormal
