@@ -105,6 +105,7 @@ struct Abi<float> {
     static constexpr auto transform = petal_transform_f32;
     static constexpr auto inverse_transform = petal_inverse_transform_f32;
     static constexpr auto fastica_fit = petal_fastica_fit_f32;
+    static constexpr auto fastica_deflation_fit = petal_fastica_deflation_fit_f32;
 };
 template <>
 struct Abi<double> {
@@ -113,6 +114,7 @@ struct Abi<double> {
     static constexpr auto transform = petal_transform_f64;
     static constexpr auto inverse_transform = petal_inverse_transform_f64;
     static constexpr auto fastica_fit = petal_fastica_fit_f64;
+    static constexpr auto fastica_deflation_fit = petal_fastica_deflation_fit_f64;
 };
 
 template <typename A>
@@ -312,6 +314,7 @@ public:
         return detail::transform(*ctx_, x, components_, means_, true);
     }
     int64_t n_iter = 0;  // private field in the reference, read by its tests (src/ica.rs:412)
+    bool deflation = false;  // extension: deflation scheme instead of the reference's symmetric one
 
 private:
     void inner_fit(const Matrix<A>& x, Matrix<A>* sources) {  // src/ica.rs:167-222
@@ -321,9 +324,14 @@ private:
         Matrix<A> comps(nc, x.cols);
         std::vector<A> mean((size_t)x.cols);
         double lim = 0;
-        ctx_->check(detail::Abi<A>::fastica_fit(ctx_->get(), x.data.data(), x.rows, x.cols, PETAL_ICA_LOGCOSH, 1e-4, 200,
-                                                0, w_init.data.data(), comps.data.data(), mean.data(), &n_iter, &lim,
-                                                sources ? sources->data.data() : nullptr));
+        if (deflation)  // extension: one component at a time; the reference has the symmetric scheme only
+            ctx_->check(detail::Abi<A>::fastica_deflation_fit(ctx_->get(), x.data.data(), x.rows, x.cols, PETAL_ICA_LOGCOSH,
+                                                              1e-4, 200, w_init.data.data(), comps.data.data(), mean.data(),
+                                                              &n_iter, &lim, sources ? sources->data.data() : nullptr));
+        else
+            ctx_->check(detail::Abi<A>::fastica_fit(ctx_->get(), x.data.data(), x.rows, x.cols, PETAL_ICA_LOGCOSH, 1e-4, 200,
+                                                    0, w_init.data.data(), comps.data.data(), mean.data(), &n_iter, &lim,
+                                                    sources ? sources->data.data() : nullptr));
         components_ = std::move(comps);
         means_ = std::move(mean);
     }

@@ -302,6 +302,9 @@ struct TcParams {
     const float* bias;    // tc_xb, row-major Y: per output column, added in the epilogue (nullable)
     int64_t y_cols;       // tc_xb, row-major Y: columns of a Y row that may be written (the row pitch, or the width of
                           // a column block when Y is a window of a wider matrix)
+    int nwin;             // tc_xb, row-major Y wider than one MMA N: number of n_pad-column windows of Y produced per
+                          // 256-row super-tile (B^T is [nwin * n_pad][K]); 1 = the plain kernel.  A CTA walks the windows
+                          // of a super-tile back to back, so the narrow A tile is re-read from L2, not from HBM
     int ones_col_p1;      // tc_xb, panel-major Y: 1 + index of a padding column that is written as 1.0 (valid rows) instead of
                           // 0 - the X^T Y pass that follows then delivers the column sums of X - mu for free; 0 = none
     // tc_atb outputs / decomposition
@@ -397,6 +400,7 @@ struct Group {
     int64_t row0;
     int64_t kblocks;
     int f0;
+    int win;  // tc_xb: output window (see TcParams::nwin)
 };
 
 // Position in a ring of `n` stages, advanced incrementally: a runtime `it % n`, `it / n` pair costs an
@@ -428,11 +432,13 @@ __device__ __forceinline__ bool get_group(const TcParams& p, int64_t g, Group& o
         out.f0 = fg * 256;
         return true;
     } else {
-        const int64_t item = (int64_t)blockIdx.x + g * (int64_t)gridDim.x;
+        const uint32_t tile_round = (uint32_t)g / (uint32_t)p.nwin;
+        const int64_t item = (int64_t)blockIdx.x + (int64_t)tile_round * (int64_t)gridDim.x;
         if (item * 256 >= p.n) return false;
         out.row0 = item * 256;
         out.kblocks = (p.K + kKB - 1) / kKB;
         out.f0 = 0;
+        out.win = (int)((uint32_t)g - tile_round * (uint32_t)p.nwin);
         return true;
     }
 }
@@ -519,7 +525,9 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
         const int xb_chunks = ATB ? 0 : (panel ? (n_pad - half * 16 + 31) / 32 : n_pad / 16);
         uint32_t pend_gi = 0;
         int pend_next = 0;
-        auto store_rowmajor_chunk = [&](int64_t row0, int c0, const float* w) {
+        int pend_wcol = 0;  // first column of the pending super-tile's output window
+        auto store_rowmajor_chunk = [&](int64_t row0, int c0w, const float* w) {
+            const int c0 = pend_wcol + c0w;
             // 16x256b pattern: four lanes hold 8 consecutive columns of one row, so every store instruction writes
             // whole 32 B sectors (8 rows x 32 B).  This warp covers lanes 16*half .. 16*half+15 of its quarter.
             const int t0 = lane & 3, t1 = lane >> 2;
@@ -927,6 +935,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                         pend_ch = chains++;
                         pend_flush = (kb == g.kblocks - 1);
                         pend_row0 = g.row0;
+                        pend_wcol = g.win * n_pad;
                     }
                   }
                 } else {
@@ -958,6 +967,7 @@ __device__ __forceinline__ void transform_role(const TcParams& p, uint8_t* base_
                 while (pend_on) xb_drain_step();  // whatever is left of the previous super-tile
                 pend_on = true;
                 pend_row0 = g.row0;
+                pend_wcol = g.win * n_pad;
                 pend_gi = (uint32_t)gi;
                 pend_next = 0;
                 if (acc_bufs != 2)
@@ -1160,8 +1170,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         } else {
                             const int k0 = (int)(kb * kKB);
                             mbar_expect_tx(fullb, 2u * L.stage_b);
-                            tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, k0, 0, fullb);
-                            tma_load_2d(base + L.blo + (uint32_t)sb * L.stage_b, &p.map_blo, k0, 0, fullb);
+                            tma_load_2d(base + L.bhi + (uint32_t)sb * L.stage_b, &p.map_bhi, k0, g.win * n_pad, fullb);
+                            tma_load_2d(base + L.blo + (uint32_t)sb * L.stage_b, &p.map_blo, k0, g.win * n_pad, fullb);
                         }
                     }
                 }
@@ -1419,29 +1429,34 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
                   bool b_trans, int64_t L, const float* mu, float* Y, int64_t ldy, double* sumsq,
                   bool y_panel = false, float* Y_lo_panel = nullptr, int precise = -1, const float* bias = nullptr,
                   int64_t y_cols = -1, int ones_col = -1) {
-    const int n_pad = round_up(L, 16);
+    // L > 128 (row-major Y only): windows of 128 output columns walked inside the kernel (TcParams::nwin)
+    const int nwin = (L > 128) ? (int)ceil_div(L, 128) : 1;
+    if (nwin > 1 && (y_panel || sumsq != nullptr)) linalg_error("tc_xb: wide outputs are row-major, without a sum of squares");
+    const int n_pad = nwin > 1 ? 128 : round_up(L, 16);
+    const int b_rows = nwin * n_pad;  // rows of the B^T operand arrays
     int stages = 0, stages_b = 0;
     if (!pick_stages(false, n_pad, false, stages, stages_b)) linalg_error("tc_xb: no pipeline configuration fits in shared memory");
     const int64_t Kp = round_up(K, 32);
-    DBuf<float> bhi(ctx, (size_t)(n_pad * Kp)), blo(ctx, (size_t)(n_pad * Kp)), mup(ctx, (size_t)Kp);
+    DBuf<float> bhi(ctx, (size_t)(b_rows * Kp)), blo(ctx, (size_t)(b_rows * Kp)), mup(ctx, (size_t)Kp);
     if (kCrossEnabled)
-        prep_b_cross_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * (Kp / 2), 256), 256, 0, ctx->stream>>>(
-            B, ldb, b_trans ? 1 : 0, K, Kp, (int)L, n_pad, bhi.p, reinterpret_cast<uint32_t*>(blo.p));
+        prep_b_cross_kernel<TS><<<(unsigned)ceil_div((int64_t)b_rows * (Kp / 2), 256), 256, 0, ctx->stream>>>(
+            B, ldb, b_trans ? 1 : 0, K, Kp, (int)L, b_rows, bhi.p, reinterpret_cast<uint32_t*>(blo.p));
     else
-        prep_b_kernel<TS><<<(unsigned)ceil_div((int64_t)n_pad * Kp, 256), 256, 0, ctx->stream>>>(B, ldb, b_trans ? 1 : 0, K, Kp,
-                                                                                                (int)L, n_pad, bhi.p, blo.p);
+        prep_b_kernel<TS><<<(unsigned)ceil_div((int64_t)b_rows * Kp, 256), 256, 0, ctx->stream>>>(B, ldb, b_trans ? 1 : 0, K, Kp,
+                                                                                                 (int)L, b_rows, bhi.p, blo.p);
     check_launch(ctx);
     prep_mu_kernel<<<(unsigned)ceil_div(Kp, 256), 256, 0, ctx->stream>>>(mu, K, Kp, mup.p);
     check_launch(ctx);
     TcParams p;
     std::memset(&p, 0, sizeof p);
     p.map_x = make_map_2d(A, (uint64_t)K, (uint64_t)n, (uint64_t)lda, 32, 256, true);
-    p.map_bhi = make_map_2d(bhi.p, (uint64_t)Kp, (uint64_t)n_pad, (uint64_t)Kp, 32, (uint32_t)n_pad, true);
-    p.map_blo = make_map_2d(blo.p, (uint64_t)Kp, (uint64_t)n_pad, (uint64_t)Kp, 32, (uint32_t)n_pad, true);
+    p.map_bhi = make_map_2d(bhi.p, (uint64_t)Kp, (uint64_t)b_rows, (uint64_t)Kp, 32, (uint32_t)n_pad, true);
+    p.map_blo = make_map_2d(blo.p, (uint64_t)Kp, (uint64_t)b_rows, (uint64_t)Kp, 32, (uint32_t)n_pad, true);
     p.mu_pad = mup.p;
     p.n = n;
     p.K = K;
     p.n_pad = n_pad;
+    p.nwin = nwin;
     p.L = (int)L;
     p.stages = stages;
     p.stages_b = stages_b;
@@ -1466,7 +1481,7 @@ void launch_tc_xb(petal_ctx* ctx, const float* A, int64_t lda, int64_t n, int64_
     const SmemLayout lay = make_layout(false, n_pad, stages, stages_b);
     const int64_t items = ceil_div(n, 256);
     const int grid = (int)std::min<int64_t>(items, ctx->sm_count);
-    KTimer kt(ctx, K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny", (double)n * (K + L) * sizeof(float));
+    KTimer kt(ctx, nwin > 1 ? "tc_xb_f32_wide" : (K >= 256 ? "tc_xb_f32" : "tc_xb_f32_skinny"), (double)n * (K + L) * sizeof(float));
     switch (mode * 2 + (y_panel ? 1 : 0)) {
         case 6: launch_kernel<false, 0, false, 3>(ctx, p, grid, lay.total); break;
         case 7: launch_kernel<false, 0, true, 3>(ctx, p, grid, lay.total); break;

@@ -109,6 +109,41 @@ def main():
     _, defect = oica.match_rows(ic2.components, or2.components)
     report("fastica f32 uneven shards around 1024 rows", defect < 1e-3, f"defect {defect:.2e} n_iter {ic2.n_iter}/{or2.n_iter}")
 
+    # host shards streamed out of core (two ring slots, 2048-row chunks) on every rank: same collectives, same results
+    ctx.set_host_staging(2, 2048 * 256 * 4)
+    r0, r1 = shard_rows(x32.shape[0], rank, world)
+    rp3 = pd.RandomizedPcaBuilder.new(16).seed(seed).n_power_iter(4).build()
+    y3 = rp3.fit_transform(np.ascontiguousarray(x32[r0:r1]))
+    st = ctx.host_stream_stats()
+    err = np.max(np.abs(rp3.singular_values() - rref.singular_values()) / rref.singular_values())
+    report("rpca f32 out-of-core shards", err < 1e-4 and st["out_of_core"] and st["traversals"] == 5,
+           f"rel err {err:.2e} traversals {st['traversals']}")
+    report("rpca f32 out-of-core scores", np.allclose(y3[:, :8], yr32[:, :8], atol=2e-3 * sc))
+    ctx.set_host_staging(2, 1024 * 96 * 8)
+    r0, r1 = shard_rows(x.shape[0], rank, world)
+    m3 = pd.Pca.new(6)
+    y3 = m3.fit_transform(np.ascontiguousarray(x[r0:r1]))
+    err = np.max(np.abs(m3.singular_values() - ref.singular_values()) / ref.singular_values())
+    report("pca f64 out-of-core shards", err < 1e-10 and np.allclose(y3, yr[r0:r1], atol=1e-8 * np.abs(yr).max()),
+           f"rel err {err:.2e} traversals {ctx.host_stream_stats()['traversals']}")
+    ctx.set_host_staging(0, 1 << 30)
+
+    # deflation FastICA f64 over row shards: whitening read back (max_iter = 0, w_init = I), the oracle's deflation run in
+    # those coordinates (see tests/test_gpu_deflation.py)
+    r0, r1 = shard_rows(xi.shape[0], rank, world)
+    xloc = np.ascontiguousarray(xi[r0:r1])
+    mk = pd.FastIca(pd.Pcg.from_seed(seed), max_iter=0, algorithm=pd.DEFLATION)
+    mk.fit(xloc, np.eye(6))
+    w6 = Mcg128Xsl64.from_seed_u128(seed).normal_matrix(6, 6)
+    x1 = (mk.components @ (xi - mk.means).T) * np.sqrt(xi.shape[0])
+    w_ref, it_ref = oica.ica_def(x1, 1e-4, 200, w6, "logcosh")
+    md = pd.FastIca(pd.Pcg.from_seed(seed), algorithm=pd.DEFLATION)
+    md.fit(xloc, w6)
+    cref = w_ref @ mk.components
+    sgn = np.sign(np.sum(md.components * cref, axis=1, keepdims=True))
+    derr = np.max(np.abs(md.components - sgn * cref)) / np.abs(cref).max()
+    report("fastica deflation f64 over shards", derr < 1e-7 and md.n_iter == it_ref, f"err {derr:.2e} n_iter {md.n_iter}/{it_ref}")
+
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{ctx.device}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
