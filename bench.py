@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--host-staging", type=int, default=0, choices=[0, 1, 2],
                     help="e2e arm: how the host X reaches HBM - 0 resident copy when it fits (chunks consumed as they land), "
                          "1 always resident, 2 out-of-core (X re-streamed through a two-slot ring by every traversal)")
+    ap.add_argument("--no-host-gram", action="store_true",
+                    help="e2e arm, randomized PCA: plain pass sequence instead of power iterations on the ingest-time Gram matrix")
     ap.add_argument("--host-chunk-mb", type=int, default=0, help="e2e arm: H2D chunk size (default: the library's 1 GiB)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-rows", type=int, default=0)
@@ -482,6 +484,8 @@ def main():
             torch.cuda.empty_cache()
             ctx.trim()
             ctx.set_host_staging(args.host_staging, args.host_chunk_mb << 20)
+            if args.no_host_gram:
+                ctx.set_host_gram(0)
             for _ in range(min(args.warmup, 1)):
                 step(xh)
             barrier()
@@ -501,9 +505,16 @@ def main():
                    "d2h_bytes_per_step": int(d2h), "rows_per_gpu": n_e2e, "ms_per_step": dt * 1e3,
                    "numa_bound_cpus": numa_cpus,
                    "timing": "wall clock around the public API call (includes H2D of X from pinned host memory)"}
+            if algorithm != "ica" and n_e2e == n and model is not None:
+                # the host-fed fit (chunked ingest, power iterations on the ingest-time Gram matrix) against the
+                # device-resident fit of the same X: same model up to rounding
+                s_dev = np.asarray(model.singular_values(), np.float64)
+                s_e2e = np.asarray(m.singular_values(), np.float64)
+                e2e["sigma_max_rel_diff_vs_device_fit"] = float(np.max(np.abs(s_e2e - s_dev) / s_dev))
             st = ctx.host_stream_stats()
             e2e["host_staging"] = {"mode": "out-of-core ring" if st["out_of_core"] else "resident copy, chunks consumed as they land",
                                    "traversals_of_x": st["traversals"], "h2d_bytes_moved": st["h2d_bytes"],
+                                   "power_iterations_on_ingest_gram": bool(ctx.set_host_gram(-1)) and algorithm == "rpca" and world == 1,
                                    "chunk_bytes": (args.host_chunk_mb << 20) or (1 << 30)}
             if st["out_of_core"]:
                 e2e["h2d_bytes_per_step"] = int(st["h2d_bytes"])

@@ -40,6 +40,7 @@ SYMBOLS = {
     "petal_ctx_set_f32_engine": (c_int, [c_vp, c_int]),
     "petal_ctx_set_f64_engine": (c_int, [c_vp, c_int]),
     "petal_ctx_set_host_staging": (c_int, [c_vp, c_int, c_i64]),
+    "petal_ctx_set_host_gram": (c_int, [c_vp, c_int]),
     "petal_ctx_host_stream_stats": (c_int, [c_vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_int)]),
     "petal_ctx_set_profiling": (c_int, [c_vp, c_int]),
     "petal_ctx_profile_json": (c_i64, [c_vp, C.c_char_p, c_i64]),

@@ -108,6 +108,10 @@ class Context:
         2 = always out-of-core (X re-streamed through a two-slot ring by every pass).  chunk_bytes: H2D chunk size."""
         return int(self.lib.petal_ctx_set_host_staging(self.handle, int(mode), int(chunk_bytes)))
 
+    def set_host_gram(self, enable: int = -1) -> int:
+        """Randomized PCA on a host X: power iterations on the Gram matrix accumulated during the ingest (default on)."""
+        return int(self.lib.petal_ctx_set_host_gram(self.handle, int(enable)))
+
     def host_stream_stats(self) -> dict:
         """H2D bytes, traversals of X and the mode of the last call that was given a host X."""
         b, t, r = C.c_int64(0), C.c_int64(0), C.c_int(0)

@@ -71,6 +71,7 @@ struct petal_ctx {
     bool status_armed = false;  // a kernel that may raise dev_status was launched during this call
     // host-resident X (row_stream.cuh): 0 = auto (resident copy when it fits, else out-of-core ring), 1 = always a
     // resident copy, 2 = always the two-slot ring; rows of X per H2D chunk are derived from host_chunk_bytes
+    int host_gram = 1;    // randomized PCA on a host-fed X: power iterations on the Gram matrix taken during the ingest
     int host_staging = 0;
     int64_t host_chunk_bytes = (int64_t)1 << 30;
     cudaStream_t copy_stream = nullptr;   // created on first use

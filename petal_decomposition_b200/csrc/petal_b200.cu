@@ -719,13 +719,28 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     // sample, its panel carries a column of ones, so the X^T Y pass that follows also returns the column sums of
     // X - mu~; the exact mean mu = mu~ + delta and the exact Z = Xc^T (Xc Omega), ||Xc||_F^2 follow by rank-one
     // corrections of the small side (delta ~ sigma / sqrt(sample): no cancellation).
+    // Host-fed X (single rank): while the rows cross PCIe the GPU is idle - the transfer of a chunk takes several times
+    // as long as any pass over it - so the ingest traversal also accumulates the d x d Gram matrix G = Xc^T Xc (f64
+    // accumulation; `mean_and_gram`, one trip).  The power iterations Z <- Xc^T (Xc B) = G B (src/pca.rs:708-715) then
+    // run on the replicated small side without touching X again; only the last pair - Y = Xc B_q and C' = Xc^T Y, the
+    // products that define the result - is taken from X itself, so the singular values keep the accuracy of a direct
+    // pass (G only has to preserve the dominant subspace, like every intermediate iterate).  Resident copy: q of the
+    // q + 1 pass pairs disappear behind the transfer; out of core: 2 trips over PCIe instead of q + 1.
+    // Not used for X already in HBM, where a Gram pass (n d^2 flops) costs more than the 2q streaming passes it saves.
+    bool gram_mode = X.host && !X.loaded && ctx->world == 1 && n_iter >= 1 && d <= 2048 && n_total >= 2 * d;
+    if (const char* e = getenv("PETAL_RPCA_GRAM")) gram_mode = gram_mode && atoi(e) != 0;
+    if (ctx->host_gram == 0) gram_mode = false;
+    DBuf<double> Gm(ctx, gram_mode ? (size_t)(d * d) : 0);
+
     ColMean<T> cm;
     bool fold_mean = false;
     if constexpr (sizeof(T) == 4) {
-        fold_mean = panel && centering && n_iter >= 1 && (l % 16) != 0;
+        fold_mean = !gram_mode && panel && centering && n_iter >= 1 && (l % 16) != 0;
         if (const char* e = getenv("PETAL_FOLD_MEAN")) fold_mean = fold_mean && atoi(e) != 0;
     }
-    if (fold_mean) {
+    if (gram_mode) {
+        mean_and_gram<T>(ctx, X, d, n_total, centering, cm, Gm.p);
+    } else if (fold_mean) {
         cm.mean_d.alloc(ctx, (size_t)d);
         cm.mean_t.alloc(ctx, (size_t)d);
         DBuf<double> sum(ctx, (size_t)d + 1);
@@ -774,7 +789,26 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     if (const char* e = getenv("PETAL_ATB_FAST_ITERS")) fast_atb_iters = atoi(e);
     DBuf<double> Zd(ctx, (size_t)(d * l)), Zacc(ctx, (size_t)(d * (l + 1))), wu(ctx, (size_t)(2 * l)), sc(ctx, 2);
     if (fold_mean && !panel) linalg_error("inconsistent panel-path decision (folded mean)");
-    for (int64_t j = 0; j <= n_iter; ++j) {
+    int64_t j_first = 0;
+    if (gram_mode) {
+        // ||Xc||_F^2 = trace(G) (src/pca.rs:533); Z_1 = G Omega, Z_{i+1} = G orth(Z_i)
+        trace_kernel<<<1, 256, 0, ctx->stream>>>(Gm.p, d, tvd);
+        launch1(ctx);
+        DBuf<double> Om(ctx, (size_t)(d * l_full));
+        launch_cast<T, double>(ctx, Omega.p, Om.p, d * l_full);
+        const double* Bcur = Om.p;
+        int64_t ldb = l_full;
+        for (int64_t it = 0; it < n_iter; ++it) {
+            gemm_xb<double>(ctx, Gm.p, d, d, d, Bcur, ldb, false, l, nullptr, nullptr, Zacc.p, l);
+            PETAL_CUDA(cudaMemcpyAsync(Zd.p, Zacc.p, (size_t)(d * l) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            orthonormalize_columns(ctx, Zd.p, d, l, cutoff);
+            Bcur = Zd.p;
+            ldb = l;
+        }
+        pc.mark("power iterations on G");
+        j_first = n_iter;
+    }
+    for (int64_t j = j_first; j <= n_iter; ++j) {
         const bool last = (j == n_iter);
         const bool folded = fold_mean && j == 0;
         // accumulator of this traversal's X^T Y: Zt [d x (l + 1)] with the ones column when the mean is folded in,
@@ -1772,6 +1806,13 @@ int petal_ctx_set_host_staging(petal_ctx* ctx, int mode, int64_t chunk_bytes) {
     if (mode >= 0 && mode <= 2) ctx->host_staging = mode;
     if (chunk_bytes > 0) ctx->host_chunk_bytes = chunk_bytes;
     return ctx->host_staging;
+}
+
+int petal_ctx_set_host_gram(petal_ctx* ctx, int enable) {
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (enable >= 0) ctx->host_gram = enable ? 1 : 0;
+    return ctx->host_gram;
 }
 
 int petal_ctx_host_stream_stats(const petal_ctx* ctx, int64_t* h2d_bytes, int64_t* traversals, int* ring) {

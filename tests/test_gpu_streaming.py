@@ -27,12 +27,14 @@ def pd():
 def staging(pd):
     ctx = pd.default_context()
 
-    def set_(mode, chunk_bytes):
+    def set_(mode, chunk_bytes, gram=0):
         ctx.set_host_staging(mode, chunk_bytes)
+        ctx.set_host_gram(gram)  # 0: the plain pass sequence, whose trip counts the tests below assert
         return ctx
 
     yield set_
     ctx.set_host_staging(0, 1 << 30)
+    ctx.set_host_gram(1)
 
 
 def rel(a, b):
@@ -175,3 +177,31 @@ def test_auto_mode_keeps_small_inputs_resident(pd, staging):
     pd.RandomizedPca.with_seed(4, 1).fit(x)
     st = ctx.host_stream_stats()
     assert st["out_of_core"] is False and st["h2d_bytes"] <= 2 * x.nbytes
+
+
+@pytest.mark.parametrize("mode", [RESIDENT, RING], ids=["resident", "ring"])
+@pytest.mark.parametrize("dtype,n,d,k,q,tol", [(np.float32, 60_000, 256, 16, 4, 1e-4), (np.float32, 40_000, 1024, 64, 4, 1e-4),
+                                               (np.float64, 30_000, 128, 12, 3, 1e-9), (np.float32, 50_000, 160, 22, 7, 1e-4)])
+def test_rpca_host_gram_mode_vs_oracle(pd, staging, mode, dtype, n, d, k, q, tol):
+    """Host-fed randomized PCA with the power iterations on the Gram matrix taken during the ingest (the default for a
+    host X): 2 traversals of X whatever q - (mean, column sums, Gram) and the final (Y = Xc B_q, C' = Xc^T Y) pair, plus
+    the C' = Xc^T Y1 pass of the row-major path - and the oracle's singular values, variance ratios and subspace."""
+    x = synth.lowrank_noise(n, d, rank=40, seed=13, dtype=dtype)
+    omega = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(d, k + 10, dtype)
+    ref = opca.RandomizedPca(k, n_iter=q)
+    yr = ref.fit_transform(x.astype(np.float64), omega.astype(np.float64))
+    ctx = staging(mode, 8192 * d * x.itemsize, gram=1)
+    m = pd.RandomizedPcaBuilder.new(k).seed(RNG_SEED).n_power_iter(q).build()
+    y = m.fit_transform(x, omega)
+    st = ctx.host_stream_stats()
+    panel = dtype == np.float32
+    assert st["traversals"] == (2 if panel else 3), st
+    if mode == RING:
+        assert st["h2d_bytes"] == st["traversals"] * x.nbytes + min(n, 8192) * d * x.itemsize
+    assert rel(m.singular_values(), ref.singular_values()) < tol
+    assert rel(m.explained_variance_ratio(), ref.explained_variance_ratio()) < 2 * tol
+    assert np.allclose(m.mean(), ref.means, atol=1e-6 if dtype == np.float32 else 1e-12)
+    assert abs(m._total_variance - ref.total_variance) < (1e-5 if dtype == np.float32 else 1e-10) * ref.total_variance
+    h = min(k, 12)
+    assert opca.principal_angles(m.components()[:h], ref.components[:h]).max() < (2e-3 if dtype == np.float32 else 1e-6)
+    assert np.allclose(y[:, :h], yr[:, :h], atol=(2e-3 if dtype == np.float32 else 1e-6) * np.abs(yr).max())
