@@ -514,7 +514,7 @@ def main():
             st = ctx.host_stream_stats()
             e2e["host_staging"] = {"mode": "out-of-core ring" if st["out_of_core"] else "resident copy, chunks consumed as they land",
                                    "traversals_of_x": st["traversals"], "h2d_bytes_moved": st["h2d_bytes"],
-                                   "power_iterations_on_ingest_gram": bool(ctx.set_host_gram(-1)) and algorithm == "rpca" and world == 1,
+                                   "power_iterations_on_ingest_gram": bool(ctx.set_host_gram(-1)) and algorithm == "rpca",
                                    "chunk_bytes": (args.host_chunk_mb << 20) or (1 << 30)}
             if st["out_of_core"]:
                 e2e["h2d_bytes_per_step"] = int(st["h2d_bytes"])

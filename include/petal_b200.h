@@ -83,7 +83,7 @@ int petal_ctx_set_f64_engine(petal_ctx* ctx, int engine);
  * A host `out` of inverse_transform larger than a chunk is produced and drained chunk by chunk in the same way.
  * Returns the mode now in force (negative `mode` only queries). */
 int petal_ctx_set_host_staging(petal_ctx* ctx, int mode, int64_t chunk_bytes);
-/* Randomized PCA on a host-fed X (single rank, d <= 2048, at least one power iteration): the ingest traversal also
+/* Randomized PCA on a host-fed X (every rank's shard a host buffer, d <= 2048, at least one power iteration): the ingest traversal also
  * accumulates the Gram matrix G = Xc^T Xc while the GPU would otherwise wait for PCIe, the power iterations
  * Z <- Xc^T (Xc B) = G B (src/pca.rs:708-715) run on the small side, and only the last pair of products (the ones
  * that define the result) is taken from X: 2 traversals instead of q + 1.  1 = on (default), 0 = off (the plain pass

@@ -154,7 +154,7 @@ __global__ void fold_mean_commit_kernel(const double* __restrict__ Zt, int64_t d
     mean_d[j] = (double)mt;
 }
 
-__global__ void trace_kernel(const double* __restrict__ G, int64_t d, double* __restrict__ out) {
+__global__ void trace_kernel(const double* __restrict__ G, int64_t d, double* __restrict__ out, double scale = 1.0) {
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < d; i += blockDim.x) s += G[i * d + i];
     __shared__ double red[256];
@@ -163,7 +163,7 @@ __global__ void trace_kernel(const double* __restrict__ G, int64_t d, double* __
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < blockDim.x; ++i) t += red[i];
-        *out = t;
+        *out = t * scale;
     }
 }
 
@@ -358,12 +358,14 @@ __global__ void shifted_mean_kernel(const double* __restrict__ sum, const double
     mean_t[j] = mt;
     mean_d[j] = (double)mt;
 }
+// `all_ranks_one_trip`: the caller has established (global_info) that EVERY rank is host-fed, so all of them take the
+// one-trip route and issue its collectives; without that, several ranks keep the plain order (host-fed and device-fed
+// ranks then issue identical collectives).
 template <typename T>
-void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, bool centering, ColMean<T>& cm, double* G) {
-    const bool one_trip = X.host && !X.loaded;  // rank-uniform by construction only on a single rank; see below
-    if (!one_trip || ctx->world > 1 || !centering) {
-        // (several ranks: the provisional mean would need its own collective; the plain order keeps the collectives of
-        //  host-fed and device-fed ranks identical)
+void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, bool centering, ColMean<T>& cm, double* G,
+                   bool all_ranks_one_trip = false) {
+    const bool one_trip = all_ranks_one_trip || (ctx->world == 1 && X.host && !X.loaded);
+    if (!one_trip || !centering) {
         compute_mean<T>(ctx, X, d, n_total, centering, cm);
         PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
         X.traverse([&](const T* Xc, int64_t, int64_t rows) { centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mu, G); });
@@ -377,9 +379,10 @@ void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, 
     DBuf<T> head_tmp;
     sum.zero();
     const int64_t rows_s = std::min<int64_t>(X.n, 8192);
-    launch_colsum<T>(ctx, X.head(rows_s, head_tmp), rows_s, d, d, sum.p);
+    if (rows_s > 0) launch_colsum<T>(ctx, X.head(rows_s, head_tmp), rows_s, d, d, sum.p);
     set_value_kernel<<<1, 1, 0, ctx->stream>>>(sum.p + d, (double)rows_s);
     launch1(ctx);
+    allreduce_sum(ctx, sum.p, (size_t)d + 1);  // the same provisional mean on every rank
     provisional_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, d, mu0.p, cm.mean_t.p);
     launch1(ctx);
     sum.zero();
@@ -388,6 +391,8 @@ void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, 
         launch_colsum<T>(ctx, Xc, rows, d, d, sum.p);
         centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mean_t.p, G);
     });
+    allreduce_sum(ctx, sum.p, (size_t)d);
+    allreduce_sum(ctx, G, (size_t)(d * d));
     launch_symmetrize(ctx, G, d);
     shifted_mean_kernel<T><<<(unsigned)ceil_div(d, 256), 256, 0, ctx->stream>>>(sum.p, mu0.p, (double)n_total, d, cm.mean_d.p,
                                                                                cm.mean_t.p, c.p, delta.p);
@@ -684,7 +689,9 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
                       n >= 1024 && d >= 32;
         if (const char* e = getenv("PETAL_PANEL")) panel_local = panel_local && atoi(e) != 0;
     }
-    const GlobalInfo ginfo = global_info(ctx, n, panel_local);
+    // rank-uniform "every rank's shard is a non-empty host buffer" (the Gram-mode decision below changes the collectives)
+    const bool host_fed_local = x_user != nullptr && n > 0 && d > 0 && !is_device_pointer(x_user) && ctx->host_gram != 0;
+    const GlobalInfo ginfo = global_info(ctx, n, panel_local, host_fed_local);
     const int64_t n_total = ginfo.n_total;
     if (n_total < k || d < k) invalid_input(dim_message(k));  // src/pca.rs:513-518
     if (n_total == 0 || d == 0) return;                        // src/pca.rs:521-525
@@ -719,7 +726,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     // sample, its panel carries a column of ones, so the X^T Y pass that follows also returns the column sums of
     // X - mu~; the exact mean mu = mu~ + delta and the exact Z = Xc^T (Xc Omega), ||Xc||_F^2 follow by rank-one
     // corrections of the small side (delta ~ sigma / sqrt(sample): no cancellation).
-    // Host-fed X (single rank): while the rows cross PCIe the GPU is idle - the transfer of a chunk takes several times
+    // Host-fed X (on every rank): while the rows cross PCIe the GPU is idle - the transfer of a chunk takes several times
     // as long as any pass over it - so the ingest traversal also accumulates the d x d Gram matrix G = Xc^T Xc (f64
     // accumulation; `mean_and_gram`, one trip).  The power iterations Z <- Xc^T (Xc B) = G B (src/pca.rs:708-715) then
     // run on the replicated small side without touching X again; only the last pair - Y = Xc B_q and C' = Xc^T Y, the
@@ -727,9 +734,8 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     // pass (G only has to preserve the dominant subspace, like every intermediate iterate).  Resident copy: q of the
     // q + 1 pass pairs disappear behind the transfer; out of core: 2 trips over PCIe instead of q + 1.
     // Not used for X already in HBM, where a Gram pass (n d^2 flops) costs more than the 2q streaming passes it saves.
-    bool gram_mode = X.host && !X.loaded && ctx->world == 1 && n_iter >= 1 && d <= 2048 && n_total >= 2 * d;
-    if (const char* e = getenv("PETAL_RPCA_GRAM")) gram_mode = gram_mode && atoi(e) != 0;
-    if (ctx->host_gram == 0) gram_mode = false;
+    bool gram_mode = ginfo.cap[1] && host_fed_local && n_iter >= 1 && d <= 2048 && n_total >= 2 * d;
+    if (const char* e = getenv("PETAL_RPCA_GRAM")) gram_mode = gram_mode && atoi(e) != 0;  // (set it on every rank)
     DBuf<double> Gm(ctx, gram_mode ? (size_t)(d * d) : 0);
 
     ColMean<T> cm;
@@ -739,7 +745,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
         if (const char* e = getenv("PETAL_FOLD_MEAN")) fold_mean = fold_mean && atoi(e) != 0;
     }
     if (gram_mode) {
-        mean_and_gram<T>(ctx, X, d, n_total, centering, cm, Gm.p);
+        mean_and_gram<T>(ctx, X, d, n_total, centering, cm, Gm.p, /*all_ranks_one_trip=*/true);
     } else if (fold_mean) {
         cm.mean_d.alloc(ctx, (size_t)d);
         cm.mean_t.alloc(ctx, (size_t)d);
@@ -792,7 +798,8 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     int64_t j_first = 0;
     if (gram_mode) {
         // ||Xc||_F^2 = trace(G) (src/pca.rs:533); Z_1 = G Omega, Z_{i+1} = G orth(Z_i)
-        trace_kernel<<<1, 256, 0, ctx->stream>>>(Gm.p, d, tvd);
+        // (G is already summed over the ranks; tv is all-reduced with C' later, so each rank carries its 1/world share)
+        trace_kernel<<<1, 256, 0, ctx->stream>>>(Gm.p, d, tvd, 1.0 / (double)ctx->world);
         launch1(ctx);
         DBuf<double> Om(ctx, (size_t)(d * l_full));
         launch_cast<T, double>(ctx, Omega.p, Om.p, d * l_full);

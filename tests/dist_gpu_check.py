@@ -109,6 +109,15 @@ def main():
     _, defect = oica.match_rows(ic2.components, or2.components)
     report("fastica f32 uneven shards around 1024 rows", defect < 1e-3, f"defect {defect:.2e} n_iter {ic2.n_iter}/{or2.n_iter}")
 
+    # (the fits above ran with the default for host shards: power iterations on the all-reduced ingest-time Gram matrix)
+    ctx.set_host_gram(0)
+    rp0 = pd.RandomizedPcaBuilder.new(16).seed(seed).n_power_iter(4).build()
+    r0, r1 = shard_rows(x32.shape[0], rank, world)
+    rp0.fit(np.ascontiguousarray(x32[r0:r1]))
+    err = np.max(np.abs(rp0.singular_values() - rref.singular_values()) / rref.singular_values())
+    d01 = np.max(np.abs(rp0.singular_values() - rp.singular_values()) / rref.singular_values())
+    report("rpca f32 plain pass sequence (host Gram off)", err < 1e-4 and d01 < 1e-4 and ctx.host_stream_stats()["traversals"] == 5,
+           f"rel err {err:.2e}, vs Gram mode {d01:.2e}, traversals {ctx.host_stream_stats()['traversals']}")
     # host shards streamed out of core (two ring slots, 2048-row chunks) on every rank: same collectives, same results
     ctx.set_host_staging(2, 2048 * 256 * 4)
     r0, r1 = shard_rows(x32.shape[0], rank, world)
@@ -116,6 +125,13 @@ def main():
     y3 = rp3.fit_transform(np.ascontiguousarray(x32[r0:r1]))
     st = ctx.host_stream_stats()
     err = np.max(np.abs(rp3.singular_values() - rref.singular_values()) / rref.singular_values())
+    ctx.set_host_gram(1)
+    rp4 = pd.RandomizedPcaBuilder.new(16).seed(seed).n_power_iter(4).build()
+    rp4.fit(np.ascontiguousarray(x32[r0:r1]))
+    st4 = ctx.host_stream_stats()
+    err4 = np.max(np.abs(rp4.singular_values() - rref.singular_values()) / rref.singular_values())
+    report("rpca f32 out-of-core shards, Gram mode", err4 < 1e-4 and st4["out_of_core"] and st4["traversals"] == 2,
+           f"rel err {err4:.2e} traversals {st4['traversals']}")
     report("rpca f32 out-of-core shards", err < 1e-4 and st["out_of_core"] and st["traversals"] == 5,
            f"rel err {err:.2e} traversals {st['traversals']}")
     report("rpca f32 out-of-core scores", np.allclose(y3[:, :8], yr32[:, :8], atol=2e-3 * sc))
