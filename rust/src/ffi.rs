@@ -39,6 +39,16 @@ extern "C" {
     pub fn petal_fastica_fit_f64(ctx: *mut PetalCtx, x: *const f64, n: i64, d: i64, fun: c_int, tol: c_double,
         max_iter: i64, lim_variant: c_int, w_init: *const f64, components: *mut f64, mean: *mut f64,
         n_iter: *mut i64, final_lim: *mut c_double, sources: *mut f64) -> c_int;
+    // extensions: deflation scheme; how a host `x` (the caller's ArrayBase) reaches HBM
+    pub fn petal_fastica_deflation_fit_f32(ctx: *mut PetalCtx, x: *const f32, n: i64, d: i64, fun: c_int, tol: c_double,
+        max_iter: i64, w_init: *const f32, components: *mut f32, mean: *mut f32, n_iter: *mut i64,
+        final_lim: *mut c_double, sources: *mut f32) -> c_int;
+    pub fn petal_fastica_deflation_fit_f64(ctx: *mut PetalCtx, x: *const f64, n: i64, d: i64, fun: c_int, tol: c_double,
+        max_iter: i64, w_init: *const f64, components: *mut f64, mean: *mut f64, n_iter: *mut i64,
+        final_lim: *mut c_double, sources: *mut f64) -> c_int;
+    pub fn petal_ctx_set_host_staging(ctx: *mut PetalCtx, mode: c_int, chunk_bytes: i64) -> c_int;
+    pub fn petal_ctx_set_host_gram(ctx: *mut PetalCtx, enable: c_int) -> c_int;
+    pub fn petal_ctx_host_stream_stats(ctx: *const PetalCtx, h2d_bytes: *mut i64, traversals: *mut i64, ring: *mut c_int) -> c_int;
 }
 
 #[allow(dead_code)]
