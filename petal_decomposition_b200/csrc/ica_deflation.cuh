@@ -26,14 +26,45 @@ constexpr int kMaxWordsPerLane = 32;  // row elements a lane keeps in registers 
 __device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // out[i] = sum_e M[i][e] v[e] for rows i < rows of a row-major matrix: one warp per row, coalesced, shuffle-reduced
 __device__ __forceinline__ void cta_matvec(const double* __restrict__ M, int rows, int cols, const double* v, double* out) {
+    // four rows per trip: their loads are in flight together (the kernel is a chain of L2 latencies, not of flops)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < rows; i += kThreads / 32) {
-        double a = 0.0;
-        for (int e = lane; e < cols; e += 32) a += M[(int64_t)i * cols + e] * v[e];
+    constexpr int W = kThreads / 32, R = 4;
+    for (int i0 = warp; i0 < rows; i0 += W * R) {
+        double a[R];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) out[i] = a;
+        for (int r = 0; r < R; ++r) a[r] = 0.0;
+        for (int e = lane; e < cols; e += 32) {
+            const double ve = v[e];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = i0 + r * W;
+                if (i < rows) a[r] += M[(int64_t)i * cols + e] * ve;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+            if (lane == 0 && i0 + r * W < rows) out[i0 + r * W] = a[r];
+        }
     }
+}
+// out[e] = sum_i M[i][e] c[i] for e < cols (columns of a row-major matrix): thread per column, coalesced, eight rows in
+// flight per thread
+__device__ __forceinline__ double col_dot(const double* __restrict__ M, int rows, int cols, const double* c, int e) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = 0;
+    for (; i + 8 <= rows; i += 8) {
+        double m[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m[u] = M[(int64_t)(i + u) * cols + e];
+        a0 += m[0] * c[i] + m[4] * c[i + 4];
+        a1 += m[1] * c[i + 1] + m[5] * c[i + 5];
+        a2 += m[2] * c[i + 2] + m[6] * c[i + 6];
+        a3 += m[3] * c[i + 3] + m[7] * c[i + 7];
+    }
+    for (; i < rows; ++i) a0 += M[(int64_t)i * cols + e] * c[i];
+    return (a0 + a1) + (a2 + a3);
 }
 
 // state[0] lim, state[1] iterations done for the current component, state[2] 1 = converged (kernels of the batch that
@@ -194,8 +225,7 @@ defl_update_kernel(double* __restrict__ hacc, const double* __restrict__ K1, con
     __syncthreads();
     double ss = 0.0;
     for (int e = tid; e < nc; e += kThreads) {
-        double v = w1[e];
-        for (int i = 0; i < j; ++i) v -= coef[i] * W[(int64_t)i * nc + e];
+        const double v = w1[e] - col_dot(W, j, nc, coef, e);
         w1[e] = v;
         ss += v * v;
     }
@@ -210,15 +240,7 @@ defl_update_kernel(double* __restrict__ hacc, const double* __restrict__ K1, con
     const double lim = fabs(fabs(dt) - 1.0);
     for (int e = tid; e < nc; e += kThreads) w[e] = w1[e];
     __syncthreads();
-    for (int e = tid; e < d; e += kThreads) {
-        double a = 0.0;
-        if (K1) {
-            for (int i = 0; i < nc; ++i) a += K1[(int64_t)i * d + e] * w1[i];
-        } else {
-            a = w1[e];
-        }
-        wt[e] = (T)a;
-    }
+    for (int e = tid; e < d; e += kThreads) wt[e] = (T)(K1 ? col_dot(K1, nc, d, w1, e) : w1[e]);
     for (int e = tid; e < d + 1; e += kThreads) hacc[e] = 0.0;
     if (tid == 0) {
         state[0] = lim;

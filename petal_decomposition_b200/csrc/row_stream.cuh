@@ -94,10 +94,19 @@ struct RowStream {
         rows_each = std::max<int64_t>(32, ((want + 31) / 32) * 32);
         slot_rows = rows_each + kMinChunkRows;
         ensure_copy_stream(ctx);
-        if (ring)
-            slots.alloc(ctx, (size_t)(2 * slot_rows * d));
-        else
-            full.alloc(ctx, (size_t)(n * d));
+        if (!ring) {
+            try {
+                full.alloc(ctx, (size_t)(n * d));
+            } catch (const Error&) {
+                // the estimate of what fits was too optimistic (fragmentation, another process on the device): go out
+                // of core instead of failing, unless the caller insisted on a resident copy
+                cudaGetLastError();
+                full.p = nullptr;
+                if (mode == 1) throw;
+                ring = true;
+            }
+        }
+        if (ring) slots.alloc(ctx, (size_t)(2 * slot_rows * d));
         // the buffers are stream-ordered allocations of the compute stream: the copy stream may touch them only after
         // the allocation point
         PETAL_CUDA(cudaEventRecord(ctx->copy_ev[4], ctx->stream));
