@@ -57,6 +57,11 @@ public:
         static std::shared_ptr<Context> c = std::make_shared<Context>(0);
         return c;
     }
+    // How a host Matrix<A> reaches HBM (petal_b200.h): 0 resident copy when it fits, else out of core; 1 resident;
+    // 2 out of core (two ring slots).  chunk_bytes <= 0 keeps the current H2D chunk size.
+    int set_host_staging(int mode, int64_t chunk_bytes = 0) { return petal_ctx_set_host_staging(ctx_, mode, chunk_bytes); }
+    // Randomized PCA on host data: power iterations on the Gram matrix accumulated during the ingest (default on).
+    int set_host_gram(int enable) { return petal_ctx_set_host_gram(ctx_, enable); }
 
 private:
     petal_ctx* ctx_ = nullptr;

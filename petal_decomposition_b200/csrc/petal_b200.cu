@@ -308,10 +308,14 @@ void compute_mean(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, b
 
 // G[d x d] (f64) += (X - mu)^T (X - mu) over `n` rows (this rank's partial; upper tiles only on the symmetric engines)
 template <typename T>
-void centered_gram_acc(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G) {
+void centered_gram_acc(petal_ctx* ctx, const T* X, int64_t n, int64_t d, int64_t ld, const T* mu, double* G,
+                       bool allow_tc = true) {
     if constexpr (sizeof(T) == 4) {
-        // narrow f32 Gram (d <= 128): one tcgen05 pass, both operands centred on load
-        if (ctx->f32_engine == 1 && tc::atb_supported(X, ld, d, X, ld, d, n) && is_aligned16(mu)) {
+        // narrow f32 Gram (d <= 128): one tcgen05 pass, both operands centred on load.  Above 80 columns that pass
+        // runs with long accumulation chains, whose truncation bias shows on sums of squares (the diagonal, i.e. the
+        // total variance) at the 1e-5 level: callers that report trace(G) ask for the SIMT kernel (fp32-exact
+        // products, f64 flush every 8192 rows) instead.
+        if (allow_tc && ctx->f32_engine == 1 && tc::atb_supported(X, ld, d, X, ld, d, n) && is_aligned16(mu)) {
             tc::launch_tc_atb(ctx, X, ld, d, mu, X, ld, d, n, G, d, false, nullptr, mu);
             return;
         }
@@ -363,12 +367,12 @@ __global__ void shifted_mean_kernel(const double* __restrict__ sum, const double
 // ranks then issue identical collectives).
 template <typename T>
 void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, bool centering, ColMean<T>& cm, double* G,
-                   bool all_ranks_one_trip = false) {
+                   bool all_ranks_one_trip = false, bool allow_tc = true) {
     const bool one_trip = all_ranks_one_trip || (ctx->world == 1 && X.host && !X.loaded);
     if (!one_trip || !centering) {
         compute_mean<T>(ctx, X, d, n_total, centering, cm);
         PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
-        X.traverse([&](const T* Xc, int64_t, int64_t rows) { centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mu, G); });
+        X.traverse([&](const T* Xc, int64_t, int64_t rows) { centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mu, G, allow_tc); });
         allreduce_sum(ctx, G, (size_t)(d * d));
         launch_symmetrize(ctx, G, d);
         return;
@@ -389,7 +393,7 @@ void mean_and_gram(petal_ctx* ctx, RowStream<T>& X, int64_t d, int64_t n_total, 
     PETAL_CUDA(cudaMemsetAsync(G, 0, (size_t)(d * d) * sizeof(double), ctx->stream));
     X.traverse([&](const T* Xc, int64_t, int64_t rows) {
         launch_colsum<T>(ctx, Xc, rows, d, d, sum.p);
-        centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mean_t.p, G);
+        centered_gram_acc<T>(ctx, Xc, rows, d, d, cm.mean_t.p, G, allow_tc);
     });
     allreduce_sum(ctx, sum.p, (size_t)d);
     allreduce_sum(ctx, G, (size_t)(d * d));
@@ -691,7 +695,8 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     }
     // rank-uniform "every rank's shard is a non-empty host buffer" (the Gram-mode decision below changes the collectives)
     const bool host_fed_local = x_user != nullptr && n > 0 && d > 0 && !is_device_pointer(x_user) && ctx->host_gram != 0;
-    const GlobalInfo ginfo = global_info(ctx, n, panel_local, host_fed_local);
+    const bool dev_fed_local = x_user != nullptr && n > 0 && d > 0 && is_device_pointer(x_user) && ctx->host_gram != 0;
+    const GlobalInfo ginfo = global_info(ctx, n, panel_local, host_fed_local, dev_fed_local);
     const int64_t n_total = ginfo.n_total;
     if (n_total < k || d < k) invalid_input(dim_message(k));  // src/pca.rs:513-518
     if (n_total == 0 || d == 0) return;                        // src/pca.rs:521-525
@@ -733,19 +738,48 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     // products that define the result - is taken from X itself, so the singular values keep the accuracy of a direct
     // pass (G only has to preserve the dominant subspace, like every intermediate iterate).  Resident copy: q of the
     // q + 1 pass pairs disappear behind the transfer; out of core: 2 trips over PCIe instead of q + 1.
-    // Not used for X already in HBM, where a Gram pass (n d^2 flops) costs more than the 2q streaming passes it saves.
+    // For X already in HBM the route is taken only when it is cheaper in passes over X (gram_dev below).
     bool gram_mode = ginfo.cap[1] && host_fed_local && n_iter >= 1 && d <= 2048 && n_total >= 2 * d;
-    if (const char* e = getenv("PETAL_RPCA_GRAM")) gram_mode = gram_mode && atoi(e) != 0;  // (set it on every rank)
-    DBuf<double> Gm(ctx, gram_mode ? (size_t)(d * d) : 0);
+    // X already in HBM (on every rank), f32 tcgen05 path: the same route pays when G costs fewer passes over X than the
+    // power iterations it replaces.  G is taken in 64-column windows, G[:, w] = Xc^T Xc[:, w], each one precise tc_atb
+    // pass with the window of X itself as the (row-major, centred-on-load) Y operand - the kernel quality of the X^T Y
+    // passes they stand in for; a window pass costs ~1.25 plain passes (the Y tile is transposed by the transform warps),
+    // the mean one 0.6-pass column sum.  d = 256 (c5), q = 4: 4 windows + final pair against 5 pairs.
+    bool gram_dev = false;
+    if constexpr (sizeof(T) == 4) {
+        const double gwin = (double)ceil_div(d, 64);
+        gram_dev = ginfo.cap[2] && dev_fed_local && panel && n_iter >= 2 && n_total >= 2 * d && d % 4 == 0 &&
+                   1.25 * gwin < 2.0 * (double)n_iter - 1.1 && tc::atb_supported(x_user, d, d, x_user, d, 64, n);
+        // (rank-uniform: `panel` already says that every rank's shard has >= 1024 rows and is 16 B aligned)
+    }
+    if (const char* e = getenv("PETAL_RPCA_GRAM")) {  // (set it on every rank)
+        gram_mode = gram_mode && atoi(e) != 0;
+        gram_dev = gram_dev && atoi(e) != 0;
+    }
+    const bool gram_any = gram_mode || gram_dev;
+    DBuf<double> Gm(ctx, gram_any ? (size_t)(d * d) : 0);
 
     ColMean<T> cm;
     bool fold_mean = false;
     if constexpr (sizeof(T) == 4) {
-        fold_mean = !gram_mode && panel && centering && n_iter >= 1 && (l % 16) != 0;
+        fold_mean = !gram_any && panel && centering && n_iter >= 1 && (l % 16) != 0;
         if (const char* e = getenv("PETAL_FOLD_MEAN")) fold_mean = fold_mean && atoi(e) != 0;
     }
     if (gram_mode) {
-        mean_and_gram<T>(ctx, X, d, n_total, centering, cm, Gm.p, /*all_ranks_one_trip=*/true);
+        mean_and_gram<T>(ctx, X, d, n_total, centering, cm, Gm.p, /*all_ranks_one_trip=*/true, /*allow_tc=*/false);
+    } else if (gram_dev) {
+        compute_mean<T>(ctx, X, d, n_total, centering, cm);
+        Gm.zero();
+        if constexpr (sizeof(T) == 4) {
+            X.traverse([&](const T* Xc, int64_t, int64_t rows) {
+                for (int64_t c0 = 0; c0 < d; c0 += 64) {
+                    const int64_t wc = std::min<int64_t>(64, d - c0);
+                    tc::launch_tc_atb(ctx, Xc, d, d, cm.mu, Xc + c0, d, wc, rows, Gm.p + c0, d, false, nullptr,
+                                      cm.mu ? cm.mu + c0 : nullptr, -1);
+                }
+            });
+        }
+        allreduce_sum(ctx, Gm.p, (size_t)(d * d));
     } else if (fold_mean) {
         cm.mean_d.alloc(ctx, (size_t)d);
         cm.mean_t.alloc(ctx, (size_t)d);
@@ -796,7 +830,7 @@ void rpca_fit(petal_ctx* ctx, const T* x_user, int64_t n, int64_t d, int64_t k, 
     DBuf<double> Zd(ctx, (size_t)(d * l)), Zacc(ctx, (size_t)(d * (l + 1))), wu(ctx, (size_t)(2 * l)), sc(ctx, 2);
     if (fold_mean && !panel) linalg_error("inconsistent panel-path decision (folded mean)");
     int64_t j_first = 0;
-    if (gram_mode) {
+    if (gram_any) {
         // ||Xc||_F^2 = trace(G) (src/pca.rs:533); Z_1 = G Omega, Z_{i+1} = G orth(Z_i)
         // (G is already summed over the ranks; tv is all-reduced with C' later, so each rank carries its 1/world share)
         trace_kernel<<<1, 256, 0, ctx->stream>>>(Gm.p, d, tvd, 1.0 / (double)ctx->world);

@@ -95,6 +95,47 @@ def test_c5_shape_rpca_f32_vs_oracle(pd):
     assert np.allclose(m.transform(x), y, atol=2e-3 * np.abs(y).max())
 
 
+@pytest.mark.parametrize("d,q,gram", [(256, 4, True), (256, 7, True), (320, 4, True), (384, 4, False), (256, 1, False)])
+def test_rpca_device_gram_route_vs_oracle(pd, d, q, gram):
+    """X in HBM, f32: when the Gram matrix costs fewer passes over X than the power iterations it replaces (c5: d = 256,
+    q = 4 -> 4 window passes), Z <- Xc^T (Xc B) = G B runs on the small side and only the last pair of products is
+    streamed.  Launch counts say which route ran; the oracle says that both give the reference's result."""
+    import torch
+    n, k = 200_000, 32
+    x = bench.make_x_host(n, d, "f32", "rpca")
+    omega = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(d, k + 10, np.float32)
+    ref = opca.RandomizedPca(k, n_iter=q)
+    ref.fit(x.astype(np.float64), omega.astype(np.float64))
+    xd = torch.from_numpy(x).cuda()
+    ctx = pd.default_context()
+    results = {}
+    for on in (1, 0):
+        ctx.set_host_gram(on)
+        try:
+            m = pd.RandomizedPcaBuilder.new(k).seed(RNG_SEED).n_power_iter(q).build()
+            ctx.set_profiling(True)
+            ctx.profile()
+            m.fit(xd, omega)
+            prof = ctx.profile()
+        finally:
+            ctx.set_profiling(False)
+            ctx.set_host_gram(1)
+        n_atb = sum(v["count"] for kn, v in prof.items() if kn.startswith("tc_atb_f32"))
+        n_xb = sum(v["count"] for kn, v in prof.items() if kn.startswith("tc_xb_f32"))
+        if on and gram:
+            assert n_atb == -(-d // 64) + 1 and n_xb == 1, prof
+        else:
+            assert n_atb == q + 1 and n_xb == q + 1, prof
+        sr = ref.singular_values()
+        assert np.max(np.abs(m.singular_values().astype(np.float64) - sr) / sr) < 1e-4
+        assert rel(m.explained_variance_ratio(), ref.explained_variance_ratio()) < 2e-4
+        assert np.allclose(m.mean(), ref.means, atol=1e-5)
+        assert abs(m._total_variance - ref.total_variance) < 1e-5 * ref.total_variance
+        assert opca.principal_angles(m.components()[:20], ref.components[:20]).max() < 5e-3
+        results[on] = m.singular_values().astype(np.float64)
+    assert np.max(np.abs(results[1] - results[0]) / results[0]) < 2e-5
+
+
 # ------------------------------------------------------------------------------------ c4
 def test_c4_shape_pca_f64_vs_oracle(pd):
     """configs[3] at 20 000 rows: exact Pca f64, d = 4096 - CholeskyQR2 (two DMMA Gram passes, blocked Cholesky),

@@ -205,3 +205,18 @@ def test_rpca_host_gram_mode_vs_oracle(pd, staging, mode, dtype, n, d, k, q, tol
     h = min(k, 12)
     assert opca.principal_angles(m.components()[:h], ref.components[:h]).max() < (2e-3 if dtype == np.float32 else 1e-6)
     assert np.allclose(y[:, :h], yr[:, :h], atol=(2e-3 if dtype == np.float32 else 1e-6) * np.abs(yr).max())
+
+
+def test_rpca_host_gram_mode_without_centering(pd, staging):
+    n, d, k, q = 30_000, 96, 10, 3
+    x = synth.lowrank_noise(n, d, rank=30, seed=17, dtype=np.float32)
+    omega = Mcg128Xsl64.from_seed_u128(RNG_SEED).normal_matrix(d, k + 10, np.float32)
+    ref = opca.RandomizedPca(k, n_iter=q, centering=False)
+    ref.fit(x.astype(np.float64), omega.astype(np.float64))
+    ctx = staging(RING, 4096 * d * 4, gram=1)
+    m = pd.RandomizedPcaBuilder.new(k).seed(RNG_SEED).n_power_iter(q).centering(False).build()
+    m.fit(x, omega)
+    assert ctx.host_stream_stats()["traversals"] == 2
+    assert rel(m.singular_values(), ref.singular_values()) < 1e-4
+    assert np.all(m.mean() == 0)
+    assert abs(m._total_variance - ref.total_variance) < 1e-5 * ref.total_variance

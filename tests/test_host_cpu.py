@@ -196,3 +196,24 @@ def test_folded_mean_algebra():
     assert np.allclose(mu_t + delta, x.mean(axis=0), rtol=0, atol=1e-13)
     assert np.allclose(z, xc.T @ (xc @ omega), rtol=1e-12, atol=1e-9)
     assert np.isclose(tv, np.sum(xc * xc), rtol=1e-12)
+
+
+def test_gram_shift_algebra():
+    """The identity behind the one-trip (mean, Gram) ingest of a host X (petal_b200.cu::mean_and_gram): with a provisional
+    mean mu~ (first rows), c = sum(x - mu~) and delta = mu - mu~,
+        (X - mu)^T (X - mu) = G~ - c delta^T - delta c^T + n delta delta^T,   G~ = (X - mu~)^T (X - mu~),
+    also when mu is the mean ROUNDED to the data type (float32), which is the vector the later passes subtract."""
+    rng = np.random.default_rng(5)
+    n, d = 5000, 12
+    x = (rng.standard_normal((n, d)) * rng.uniform(0.5, 3.0, d) + rng.uniform(-5, 5, d)).astype(np.float32).astype(np.float64)
+    mu0 = x[:300].mean(axis=0).astype(np.float32).astype(np.float64)       # provisional mean, type T
+    mu = x.mean(axis=0).astype(np.float32).astype(np.float64)              # the mean that is subtracted, type T
+    g0 = (x - mu0).T @ (x - mu0)
+    c = x.sum(axis=0) - n * mu0
+    delta = mu - mu0
+    g = g0 - np.outer(c, delta) - np.outer(delta, c) + n * np.outer(delta, delta)
+    ref = (x - mu).T @ (x - mu)
+    assert np.allclose(g, ref, rtol=0, atol=1e-9 * np.abs(ref).max())
+    # and the power iteration identity of the Gram mode: Xc^T (Xc B) = G B
+    b = rng.standard_normal((d, 4))
+    assert np.allclose(ref @ b, (x - mu).T @ ((x - mu) @ b), rtol=1e-10)
