@@ -217,3 +217,36 @@ def test_gram_shift_algebra():
     # and the power iteration identity of the Gram mode: Xc^T (Xc B) = G B
     b = rng.standard_normal((d, 4))
     assert np.allclose(ref @ b, (x - mu).T @ ((x - mu) @ b), rtol=1e-10)
+
+
+def test_gram_route_spans_the_reference_range():
+    """The Gram route of randomized PCA (petal_b200.cu::rpca_fit): Z <- Xc^T (Xc B) evaluated as (Xc^T Xc) B.  In
+    exact arithmetic the iterates span the same spaces as the reference's range finder (src/pca.rs:707-715, restated
+    in oracle.pca.randomized_range_finder with its LU normalisation - any invertible column mixing leaves the span
+    alone), so the final projection sees the same Q up to rounding and sigma agrees."""
+    from oracle import pca as opca
+    from tests import synth
+    x = synth.lowrank_noise(3000, 40, rank=12, decay=0.7, noise=0.05, seed=2)
+    xc = x - x.mean(axis=0)
+    k, q = 6, 4
+    omega = np.random.default_rng(9).standard_normal((40, k + 10))
+    q_ref = opca.randomized_range_finder(xc, k + 10, q, omega)  # n x l, orthonormal
+    g = xc.T @ xc
+    b = omega
+    for _ in range(q):
+        b, _ = np.linalg.qr(g @ b)                               # orth(G B): d x l
+    q_gram, _ = np.linalg.qr(xc @ b)                             # the one streamed product pair starts here
+    # compare through the quantities the fit reports: singular values of Q^T Xc and the leading right subspace
+    s_ref = np.linalg.svd(q_ref.T @ xc, compute_uv=False)
+    u, s_gram, vt_gram = np.linalg.svd(q_gram.T @ xc, full_matrices=False)
+    assert np.allclose(s_gram[:k], s_ref[:k], rtol=1e-9)
+    vt_ref = np.linalg.svd(q_ref.T @ xc, full_matrices=False)[2]
+    assert opca.principal_angles(vt_gram[:k], vt_ref[:k]).max() < 1e-6
+
+
+def test_host_options_validate_without_gpu(lib):
+    import petal_decomposition_b200 as pd
+    with pytest.raises(pd.InvalidInput, match="parallel.*deflation"):
+        pd.FastIca(pd.Pcg.new(1), algorithm="symmetric")
+    assert pd.FastIcaBuilder.new().seed(3).algorithm(pd.DEFLATION).build().algorithm == "deflation"
+    assert pd.FastIca.with_seed(1).algorithm == "parallel"  # the reference's scheme is the default
