@@ -7,7 +7,10 @@ Multi-GPU (torchrun, one process per GPU): rows are sharded, every rank holds it
 shard (weak scaling); the fit is collective (NCCL all-reduce of the small replicated matrices).
 
   value  : samples/s with X resident in HBM (device-timed, CUDA events, max over ranks)
-  e2e    : samples/s through the public API with a pinned HOST X (H2D inside the call) and host outputs
+  e2e    : samples/s through the public API with a pinned HOST X (H2D inside the call) and host outputs; the library
+           streams the host X in 1 GiB chunks and consumes them as they land (`--host-staging 2`: out of core, X never
+           resident; `--no-host-gram`: plain pass sequence instead of power iterations on the ingest-time Gram matrix);
+           `e2e.sigma_max_rel_diff_vs_device_fit` compares the host-fed model with the device-resident one
   roofline, cpu_baseline, clocks, gpu_launches: see the task contract / DESIGN.md
 
 `--impl reference` times the CPU restatement of the reference (oracle/, numpy+OpenBLAS LAPACK,
